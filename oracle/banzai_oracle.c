@@ -1,0 +1,1234 @@
+/* banzai_oracle.c — TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C, single-threaded CPU restatement of the block-compression path of
+ * jgbyrne/banzai v0.3.1 (`banzai::encode`, reference lib/lib.rs:84-132 and the
+ * private stages it drives).  It exists so the CUDA path can be checked
+ * bit-for-bit; it is NEVER linked into, imported by, or called from the
+ * product (`banzai_b200/`).  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may use it.
+ *
+ * Why a restatement: the reference is Rust and no Rust toolchain exists in
+ * this image or on the GPU boxes, so the reference cannot be built or run.
+ *
+ * Parity status (see DESIGN.md "Oracle"):
+ *   - stage level: PINNED against every known-answer vector the reference's
+ *     own tests hold for this path — lib/bwt.rs:764-770 (BWT string + ptr 20),
+ *     lib/out.rs:119-131 (bit writer), lib/mtf.rs:140-155 (MTF/RLE2 vector,
+ *     dead test but valid) — plus the executable semantics of debug/bwt.py and
+ *     debug/rle1.py, the CRC-32/BZIP2 check value 0xFC891918 and libbz2 1.0.8
+ *     round trips (the reference's fuzz oracle, fuzz_targets/round_trip.rs).
+ *   - whole-stream level: the reference holds NO golden .bz2 bytes anywhere
+ *     and cannot be executed here, so exact stream bytes are pinned only by
+ *     this literal restatement cross-checked against SURVEY.md §8c V1-V11
+ *     (derived by an independent transliteration).  "whole-stream parity
+ *     unpinned by reference-emitted vectors".
+ *
+ * Third-party arithmetic: lib/crc32.rs:37-38 calls crate `crc` 3.0.0
+ * (`CRC_32_ISO_HDLC`, crc-catalog 2.1.0; not vendored in the reference).  Its
+ * published algorithm — reflected poly 0xEDB88320, init/xorout 0xFFFFFFFF — is
+ * restated in crc32_iso_hdlc() below.
+ *
+ * One deliberate deviation: the whole input is
+ * buffered, so `i < n` at lib/rle.rs:242 is a true end-of-input test and the
+ * reader-chunk-dependent truncation defect of the reference cannot occur.
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+static void orc_panic(const char *msg)
+{
+    fprintf(stderr, "banzai oracle panic: %s\n", msg);
+    abort();
+}
+
+static void *xmalloc(size_t n)
+{
+    void *p = malloc(n ? n : 1);
+    if (!p) orc_panic("out of memory");
+    return p;
+}
+
+/* ------------------------------------------------------------------------ */
+/* lib/out.rs — MSB-first bit writer                                        */
+/* ------------------------------------------------------------------------ */
+
+typedef struct {
+    uint8_t *buf;
+    size_t len, cap;
+    uint8_t strand;        /* out.rs:9  */
+    size_t strand_bits;    /* out.rs:10 */
+} BitWriter;
+
+static void bw_init(BitWriter *w)
+{
+    w->cap = 1 << 16;
+    w->buf = (uint8_t *)xmalloc(w->cap);
+    w->len = 0;
+    w->strand = 0;
+    w->strand_bits = 0;
+}
+
+static void bw_put(BitWriter *w, const uint8_t *b, size_t n)   /* BufWriter::write_all */
+{
+    if (w->len + n > w->cap) {
+        while (w->len + n > w->cap) w->cap *= 2;
+        w->buf = (uint8_t *)realloc(w->buf, w->cap);
+        if (!w->buf) orc_panic("out of memory");
+    }
+    memcpy(w->buf + w->len, b, n);
+    w->len += n;
+}
+
+/* out.rs:31-55 */
+static void bw_write_bits(BitWriter *w, uint8_t chunk, size_t num_bits)
+{
+    size_t rptr = w->strand_bits + num_bits;
+    if (rptr < 8) {
+        size_t shift = 8 - rptr;
+        w->strand |= (uint8_t)(chunk << shift);
+        w->strand_bits = rptr;
+    } else if (rptr == 8) {
+        uint8_t b = w->strand | chunk;
+        bw_put(w, &b, 1);
+        w->strand = 0;
+        w->strand_bits = 0;
+    } else {
+        size_t spill = rptr - 8;
+        uint8_t b = w->strand | (uint8_t)(chunk >> spill);
+        bw_put(w, &b, 1);
+        w->strand = (uint8_t)(chunk << (8 - spill));
+        w->strand_bits = spill;
+    }
+}
+
+/* out.rs:79-81 */
+static void bw_write_byte(BitWriter *w, uint8_t b) { bw_write_bits(w, b, 8); }
+
+/* out.rs:58-76 */
+static void bw_write_bits_u32(BitWriter *w, uint32_t chunk, size_t num_bits)
+{
+    uint8_t bytes[4] = { (uint8_t)(chunk >> 24), (uint8_t)(chunk >> 16),
+                         (uint8_t)(chunk >> 8), (uint8_t)chunk };
+    size_t full = num_bits / 8, rem = num_bits % 8;
+    size_t bptr = 3 - full;
+    if (rem != 0) bw_write_bits(w, bytes[bptr], rem);
+    bptr += 1;
+    while (bptr < 4) {
+        bw_write_byte(w, bytes[bptr]);
+        bptr += 1;
+    }
+}
+
+/* out.rs:84-104 */
+static void bw_write_bytes(BitWriter *w, const uint8_t *bytes, size_t n)
+{
+    if (w->strand_bits == 0) {
+        bw_put(w, bytes, n);
+    } else {
+        size_t rshift = w->strand_bits, lshift = 8 - w->strand_bits;
+        uint8_t strand = w->strand;
+        for (size_t k = 0; k < n; k++) {
+            uint8_t b = (uint8_t)((bytes[k] >> rshift) | strand);
+            bw_put(w, &b, 1);
+            strand = (uint8_t)(bytes[k] << lshift);
+        }
+        w->strand = strand;
+    }
+}
+
+/* out.rs:22-28 */
+static void bw_close(BitWriter *w)
+{
+    if (w->strand_bits != 0) bw_put(w, &w->strand, 1);
+}
+
+/* exported handle API so tests can replay the reference's own bit-writer KAT */
+ORC_API void *orc_bw_new(void)
+{
+    BitWriter *w = (BitWriter *)xmalloc(sizeof *w);
+    bw_init(w);
+    return w;
+}
+ORC_API void orc_bw_write_bits(void *h, uint32_t chunk, size_t nbits) { bw_write_bits((BitWriter *)h, (uint8_t)chunk, nbits); }
+ORC_API void orc_bw_write_bits_u32(void *h, uint32_t chunk, size_t nbits) { bw_write_bits_u32((BitWriter *)h, chunk, nbits); }
+ORC_API void orc_bw_write_byte(void *h, uint32_t b) { bw_write_byte((BitWriter *)h, (uint8_t)b); }
+ORC_API void orc_bw_write_bytes(void *h, const uint8_t *b, size_t n) { bw_write_bytes((BitWriter *)h, b, n); }
+ORC_API size_t orc_bw_close(void *h, uint8_t *out, size_t cap)
+{
+    BitWriter *w = (BitWriter *)h;
+    bw_close(w);
+    size_t n = w->len;
+    if (out && n <= cap) memcpy(out, w->buf, n);
+    free(w->buf);
+    free(w);
+    return n;
+}
+/* number of bits written so far (not part of the reference; used by stage tests) */
+static size_t bw_bits(const BitWriter *w) { return w->len * 8 + w->strand_bits; }
+
+/* ------------------------------------------------------------------------ */
+/* lib/crc32.rs — block checksum                                            */
+/* ------------------------------------------------------------------------ */
+
+/* crate crc 3.0.0, CRC_32_ISO_HDLC: width 32, poly 0x04C11DB7 reflected
+ * (0xEDB88320), init 0xFFFFFFFF, refin/refout true, xorout 0xFFFFFFFF. */
+static uint32_t crc32_iso_hdlc(const uint8_t *buf, size_t n)
+{
+    static uint32_t table[256];
+    static int ready = 0;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0xEDB88320u : (c >> 1);
+            table[i] = c;
+        }
+        ready = 1;
+    }
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; i++) c = table[(c ^ buf[i]) & 0xFF] ^ (c >> 8);
+    return c ^ 0xFFFFFFFFu;
+}
+
+static uint8_t reverse8(uint8_t b)      /* crc32.rs:5-22 REVERSED[] */
+{
+    b = (uint8_t)((b & 0xF0) >> 4 | (b & 0x0F) << 4);
+    b = (uint8_t)((b & 0xCC) >> 2 | (b & 0x33) << 2);
+    b = (uint8_t)((b & 0xAA) >> 1 | (b & 0x55) << 1);
+    return b;
+}
+
+/* crc32.rs:31-48 — note: like the reference, it works on a bit-reversed copy */
+ORC_API uint32_t orc_crc32(const uint8_t *buf, size_t n)
+{
+    uint8_t *rev = (uint8_t *)xmalloc(n);
+    for (size_t i = 0; i < n; i++) rev[i] = reverse8(buf[i]);
+    uint32_t chk = crc32_iso_hdlc(rev, n);
+    free(rev);
+    uint32_t sum = 0;
+    for (int i = 0; i < 32; i++) {
+        sum <<= 1;
+        sum |= (chk >> i) & 1;
+    }
+    return sum;
+}
+
+/* ------------------------------------------------------------------------ */
+/* lib/rle.rs — RLE1 of one block                                           */
+/* ------------------------------------------------------------------------ */
+
+/* rle.rs:102-253, literal 2-byte-hop loop.  `raw[0..n)` is the whole
+ * remaining input (SURVEY A-Q4).  out must hold 100000*level bytes. */
+ORC_API int orc_rle_one(const uint8_t *raw, size_t n, int level,
+                        uint8_t *out, size_t *out_len, size_t *consumed_out, uint32_t *crc)
+{
+    *out_len = 0;
+    *consumed_out = 0;
+    if (crc) *crc = 0;
+    if (level < 1 || level > 9) return -1;
+    if (n == 0) return 0;                       /* rle.rs:111-118 */
+
+    size_t bound = (size_t)100000 * (size_t)level - 1;     /* rle.rs:121 */
+    size_t olen = 0;
+#define PUSH(x) do { if (bound == 0) orc_panic("BoundedBuffer overflow"); out[olen++] = (x); bound -= 1; } while (0)
+
+    size_t floor_ = 0;
+    size_t i = 0;
+    uint8_t b = raw[i];
+
+    for (;;) {
+        if (bound == 0) {                        /* rle.rs:137-140 */
+            break;
+        } else if (bound == 1) {                 /* rle.rs:141-146 */
+            PUSH(b);
+            i += 1;
+            break;
+        } else {
+            PUSH(b);
+        }
+
+        /* margin_call (rle.rs:58-91) with the whole input buffered: remaining = n - i */
+        size_t d = n - i;
+        if (d == 0) orc_panic("unreachable margin 0");
+        if (d == 1) { i += 1; break; }
+        if (d == 2) { PUSH(raw[i + 1]); i += 2; break; }
+
+        uint8_t hop = raw[i + 2];
+        PUSH(raw[i + 1]);
+
+        if (b == hop && b == raw[i + 1]) {
+            int run = 0;
+            if (i > floor_ && b == raw[i - 1]) {           /* rle.rs:177-186 */
+                if (bound < 2) { i += 2; break; }
+                PUSH(hop);
+                i += 3;
+                run = 1;
+            }
+            if (!run && i + 3 < n) {                        /* rle.rs:189-208 */
+                uint8_t step = raw[i + 3];
+                if (b == step) {
+                    if (bound == 0) { i += 2; break; }
+                    PUSH(hop);
+                    if (bound < 2) { i += 3; break; }
+                    PUSH(step);
+                    i += 4;
+                    run = 1;
+                }
+            }
+            if (run) {                                      /* rle.rs:210-234 */
+                uint8_t rep = 0;
+                while (rep < 251) {
+                    if (i < n && raw[i] == b) { rep += 1; i += 1; continue; }
+                    break;
+                }
+                PUSH(rep);
+                floor_ = i;
+                if (i >= n) break;
+                b = raw[i];
+                continue;
+            }
+        }
+        i += 2;                                             /* rle.rs:238-239 */
+        b = hop;
+    }
+#undef PUSH
+    *out_len = olen;
+    *consumed_out = i;
+    if (crc) *crc = orc_crc32(raw, i);                      /* rle.rs:242-244 */
+    return 0;
+}
+
+/* Canonical token model of the same function: greedy
+ * RLE1 restarted at the block start + the capacity rule.  This is the model
+ * the CUDA path and its host cut-walk implement; tests prove it equal to the
+ * literal loop above. */
+ORC_API int orc_rle_canonical(const uint8_t *raw, size_t n, int level,
+                              uint8_t *out, size_t *out_len, size_t *consumed_out)
+{
+    *out_len = 0;
+    *consumed_out = 0;
+    if (level < 1 || level > 9) return -1;
+    size_t cap = (size_t)100000 * (size_t)level - 1;
+    size_t o = 0, i = 0;
+    while (i < n) {
+        size_t B = cap - o;
+        if (B == 0) break;
+        uint8_t c = raw[i];
+        size_t L = 1;
+        while (i + L < n && raw[i + L] == c && L < 255) L++;
+        if (L < 4) {                      /* literals, one at a time */
+            size_t take = L < B ? L : B;
+            for (size_t k = 0; k < take; k++) out[o++] = c;
+            i += take;
+            if (take < L) break;
+        } else if (B >= 5) {
+            out[o++] = c; out[o++] = c; out[o++] = c; out[o++] = c;
+            out[o++] = (uint8_t)(L - 4);
+            i += L;
+        } else {                          /* B in 1..4: emit min(B,3) copies and cut */
+            size_t take = B < 3 ? B : 3;
+            for (size_t k = 0; k < take; k++) out[o++] = c;
+            i += take;
+            break;
+        }
+    }
+    *out_len = o;
+    *consumed_out = i;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* lib/bwt.rs — BWT through SA-IS on the doubled block                      */
+/* ------------------------------------------------------------------------ */
+
+typedef struct {
+    uint32_t *sigma;       /* bwt.rs:116 */
+    size_t sigma_len;
+    uint32_t *sizes;       /* bwt.rs:117 */
+    uint32_t *bptrs;       /* bwt.rs:118 */
+    size_t cap;
+} Buckets;
+
+static void buckets_init(Buckets *bk)
+{
+    memset(bk, 0, sizeof *bk);
+}
+
+static void buckets_free(Buckets *bk)
+{
+    free(bk->sigma);
+    free(bk->sizes);
+    free(bk->bptrs);
+    memset(bk, 0, sizeof *bk);
+}
+
+static void buckets_reset(Buckets *bk, size_t max_sigma)
+{
+    if (max_sigma > bk->cap) {
+        free(bk->sigma);
+        free(bk->sizes);
+        free(bk->bptrs);
+        bk->sigma = (uint32_t *)xmalloc(max_sigma * sizeof(uint32_t));
+        bk->sizes = (uint32_t *)xmalloc(max_sigma * sizeof(uint32_t));
+        bk->bptrs = (uint32_t *)xmalloc(max_sigma * sizeof(uint32_t));
+        bk->cap = max_sigma;
+    }
+    memset(bk->sizes, 0, max_sigma * sizeof(uint32_t));
+    memset(bk->bptrs, 0, max_sigma * sizeof(uint32_t));
+    bk->sigma_len = 0;
+}
+
+/* bwt.rs:122-128 */
+static void buckets_heads(Buckets *bk)
+{
+    uint32_t acc = 0;
+    for (size_t k = 0; k < bk->sigma_len; k++) {
+        uint32_t w = bk->sigma[k];
+        bk->bptrs[w] = acc;
+        acc += bk->sizes[w];
+    }
+}
+
+/* bwt.rs:130-136 */
+static void buckets_tails(Buckets *bk)
+{
+    uint32_t acc = 0;
+    for (size_t k = 0; k < bk->sigma_len; k++) {
+        uint32_t w = bk->sigma[k];
+        acc += bk->sizes[w];
+        bk->bptrs[w] = acc - 1;
+    }
+}
+
+/* bwt.rs:176-184 */
+static inline void tail_push(int32_t *sa, size_t sa_len, Buckets *bk, size_t w, int32_t i)
+{
+    uint32_t *bptr = &bk->bptrs[w];
+    if ((size_t)*bptr >= sa_len) orc_panic("tail_push out of range");
+    sa[*bptr] = i;
+    *bptr = *bptr - 1u;      /* wrapping_sub */
+}
+
+/* bwt.rs:186-192 */
+static inline void head_push(int32_t *sa, size_t sa_len, Buckets *bk, size_t w, int32_t i)
+{
+    uint32_t *bptr = &bk->bptrs[w];
+    if ((size_t)*bptr >= sa_len) orc_panic("head_push out of range");
+    sa[*bptr] = i;
+    *bptr += 1;
+}
+
+#define W uint8_t
+#define FN(name) name##_u8
+#include "sais_generic.inc"
+#undef W
+#undef FN
+
+#define W uint32_t
+#define FN(name) name##_u32
+#include "sais_generic.inc"
+#undef W
+#undef FN
+
+/* Array::split (bwt.rs:20-30): the last `k` slots become the reduced string,
+ * everything before them is zeroed, the first `k` slots are the reduced SA. */
+static uint32_t *array_split(int32_t *sa, size_t len, size_t k)
+{
+    for (size_t p = 0; p < len - k; p++) sa[p] = 0;
+    return (uint32_t *)(sa + (len - k));
+}
+
+/* bwt.rs:423-518 */
+static void sais_u32(size_t sigma_size, const uint32_t *data, int32_t *sa, size_t n, Buckets *bk)
+{
+    if (!(n > 1)) orc_panic("sais: n > 1");
+
+    size_t lms_count = push_lms_u32(data, sa, n, bk, NULL);
+    if (!(lms_count <= (n >> 1))) orc_panic("sais: lms_count bound");
+
+    if (lms_count > 1) {
+        induced_sort_fwd_u32(data, sa, n, bk, 1);
+        induced_sort_bck_u32(data, sa, n, bk, 1, 0);
+
+        size_t new_sigma = 0;
+        lms_count = encode_reduced_u32(data, sa, n, &new_sigma);
+
+        if (new_sigma != lms_count) {
+            uint32_t *rdata = array_split(sa, n, lms_count);
+            buckets_build_u32(bk, rdata, lms_count, new_sigma);      /* rebuild, :484 */
+            sais_u32(new_sigma, rdata, sa, lms_count, bk);
+        } else {
+            for (size_t p = 0; p < lms_count; p++) {
+                size_t w_rank = (size_t)sa[n - lms_count + p];
+                sa[w_rank] = (int32_t)p;
+            }
+        }
+
+        decode_reduced_u32(data, sa, n, lms_count);
+
+        buckets_build_u32(bk, data, n, sigma_size);                  /* rebuild, :499 */
+        buckets_tails(bk);
+        for (size_t p = lms_count; p-- > 0;) {
+            int32_t lms_idx = sa[p];
+            sa[p] = 0;
+            tail_push(sa, n, bk, (size_t)data[lms_idx], lms_idx);
+        }
+    }
+
+    induced_sort_fwd_u32(data, sa, n, bk, 0);
+    induced_sort_bck_u32(data, sa, n, bk, 0, 1);
+}
+
+/* bwt.rs:526-756.  bwt_out must hold n bytes. Returns 0, or 1 for the
+ * degenerate early returns (n == 0 / n too large) whose ptr is usize::MAX. */
+ORC_API int orc_bwt(const uint8_t *input, size_t n, uint8_t *bwt_out, uint32_t *ptr_out,
+                    uint8_t has_byte[256])
+{
+    memset(has_byte, 0, 256);
+    *ptr_out = 0xFFFFFFFFu;
+    if (n == 0) return 1;                                   /* :536-542 */
+    if (n == 1) {                                           /* :543-550 */
+        has_byte[input[0]] = 1;
+        bwt_out[0] = input[0];
+        *ptr_out = 0;
+        return 0;
+    }
+    if (n >= (size_t)(INT32_MAX / 4) - 1) return 1;         /* :556-562 */
+
+    size_t buf_n = n * 2;                                   /* :566-567 */
+    uint8_t *data = (uint8_t *)xmalloc(buf_n);
+    memcpy(data, input, n);
+    memcpy(data + n, input, n);
+    int32_t *sa = (int32_t *)calloc(buf_n, sizeof(int32_t));
+    if (!sa) orc_panic("out of memory");
+
+    Buckets bk;
+    buckets_init(&bk);
+    buckets_build_u8(&bk, data, buf_n, 256);                /* :573 */
+
+    size_t lms_count = push_lms_u8(data, sa, buf_n, &bk, has_byte);   /* :577-606 */
+    if (!(lms_count <= (buf_n >> 1))) orc_panic("bwt: lms_count bound");
+
+    if (lms_count > 1) {                                    /* :610-649 */
+        induced_sort_fwd_u8(data, sa, buf_n, &bk, 1);
+        induced_sort_bck_u8(data, sa, buf_n, &bk, 1, 0);
+
+        size_t new_sigma = 0;
+        lms_count = encode_reduced_u8(data, sa, buf_n, &new_sigma);
+
+        if (new_sigma != lms_count) {
+            uint32_t *rdata = array_split(sa, buf_n, lms_count);
+            Buckets rbk;
+            buckets_init(&rbk);
+            buckets_build_u32(&rbk, rdata, lms_count, new_sigma);
+            sais_u32(new_sigma, rdata, sa, lms_count, &rbk);
+            buckets_free(&rbk);
+        } else {
+            for (size_t p = 0; p < lms_count; p++) {
+                size_t w_rank = (size_t)sa[buf_n - lms_count + p];
+                sa[w_rank] = (int32_t)p;
+            }
+        }
+
+        decode_reduced_u8(data, sa, buf_n, lms_count);
+
+        buckets_tails(&bk);
+        for (size_t p = lms_count; p-- > 0;) {
+            int32_t lms_idx = sa[p];
+            sa[p] = 0;
+            tail_push(sa, buf_n, &bk, (size_t)data[lms_idx], lms_idx);
+        }
+    }
+
+    /* Step 3 (:653-731): induce the BWT bytes directly */
+    buckets_heads(&bk);
+    {
+        int32_t i = (int32_t)buf_n;
+        int32_t i_sup = i - 1, i_sup2 = i - 2;
+        int32_t push_idx = (data[i_sup2] < data[i_sup]) ? ~i_sup : i_sup;
+        head_push(sa, buf_n, &bk, data[i_sup], push_idx);
+
+        for (size_t p = 0; p < buf_n; p++) {
+            i = sa[p];
+            if (i > 0) {
+                i_sup = i - 1;
+                i_sup2 = i - 2;
+                if ((size_t)i < n) sa[p] = ~(int32_t)data[i_sup];
+                else sa[p] = ~256;
+                push_idx = (i_sup2 < 0 || data[i_sup2] < data[i_sup]) ? ~i_sup : i_sup;
+                head_push(sa, buf_n, &bk, data[i_sup], push_idx);
+            } else if (i < 0) {
+                sa[p] = ~sa[p];
+            }
+        }
+    }
+
+    buckets_tails(&bk);
+    size_t start_suffix = (size_t)-1;
+    for (size_t p = buf_n; p-- > 0;) {
+        int32_t i = sa[p];
+        if (i > 0) {
+            int32_t i_sup = i - 1, i_sup2 = i - 2;
+            sa[p] = ((size_t)i < n) ? (int32_t)data[i_sup] : 256;
+            int32_t push_idx;
+            if (i_sup2 < 0) {
+                push_idx = 0;
+            } else if (data[i_sup2] > data[i_sup]) {
+                push_idx = ((size_t)i_sup < n) ? ~(int32_t)data[i_sup2] : ~256;
+            } else {
+                push_idx = i_sup;
+            }
+            tail_push(sa, buf_n, &bk, data[i_sup], push_idx);
+        } else if (i < 0) {
+            sa[p] = ~sa[p];
+        } else {
+            start_suffix = p;
+        }
+    }
+
+    /* :733-749 */
+    size_t start_ptr = (size_t)-1;
+    size_t j = 0;
+    for (size_t p = 0; p < buf_n; p++) {
+        if (p == start_suffix) {
+            if (j >= n) orc_panic("bwt: output overflow");
+            bwt_out[j] = data[n - 1];
+            start_ptr = j;
+            j += 1;
+        } else {
+            int32_t w = sa[p];
+            if (w < 256) {
+                if (j >= n || w < 0) orc_panic("bwt: output overflow");
+                bwt_out[j] = (uint8_t)w;
+                j += 1;
+            }
+        }
+    }
+    if (j != n) orc_panic("bwt: short output");
+
+    buckets_free(&bk);
+    free(sa);
+    free(data);
+    *ptr_out = (uint32_t)start_ptr;
+    return 0;
+}
+
+/* Independent model of the BWT contract (debug/bwt.py:5-27 semantics, SURVEY
+ * A-Q5): rotations ordered cyclically, equal rotations by DESCENDING start
+ * index.  O(n log n * LCP); tests use it on small / non-degenerate inputs to
+ * validate the SA-IS restatement above. */
+static const uint8_t *g_rot_data;
+static size_t g_rot_n;
+static int rot_cmp(const void *a, const void *b)
+{
+    uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b;
+    /* suffixes of S||S with an implicit smallest sentinel (bwt.py sorts l2[i:]) */
+    size_t lx = 2 * g_rot_n - x, ly = 2 * g_rot_n - y;
+    size_t l = lx < ly ? lx : ly;
+    int c = memcmp(g_rot_data + x, g_rot_data + y, l);
+    if (c) return c;
+    return lx < ly ? -1 : (lx > ly ? 1 : 0);
+}
+ORC_API int orc_bwt_naive(const uint8_t *input, size_t n, uint8_t *bwt_out, uint32_t *ptr_out,
+                          uint8_t has_byte[256])
+{
+    memset(has_byte, 0, 256);
+    *ptr_out = 0xFFFFFFFFu;
+    if (n == 0) return 1;
+    uint8_t *dbl = (uint8_t *)xmalloc(2 * n);
+    memcpy(dbl, input, n);
+    memcpy(dbl + n, input, n);
+    uint32_t *idx = (uint32_t *)xmalloc(n * sizeof(uint32_t));
+    for (size_t i = 0; i < n; i++) { idx[i] = (uint32_t)i; has_byte[input[i]] = 1; }
+    g_rot_data = dbl;
+    g_rot_n = n;
+    qsort(idx, n, sizeof(uint32_t), rot_cmp);
+    for (size_t k = 0; k < n; k++) {
+        if (idx[k] == 0) { *ptr_out = (uint32_t)k; bwt_out[k] = input[n - 1]; }
+        else bwt_out[k] = input[idx[k] - 1];
+    }
+    free(idx);
+    free(dbl);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* lib/mtf.rs — MTF + RLE2                                                  */
+/* ------------------------------------------------------------------------ */
+
+/* mtf.rs:46-65 */
+static void mtf_rle(uint16_t *output, size_t *m, uint64_t *freqs, size_t zero_count)
+{
+    size_t code = zero_count + 1;
+    for (;;) {
+        size_t bit = code & 1;
+        code >>= 1;
+        if (code == 0) break;
+        if (bit == 0) { output[(*m)++] = 0; freqs[0] += 1; }   /* RUNA */
+        else          { output[(*m)++] = 1; freqs[1] += 1; }   /* RUNB */
+    }
+}
+
+/* mtf.rs:14-121.  output must hold n + 1 symbols. */
+ORC_API int orc_mtf_and_rle(const uint8_t *buf, size_t n, const uint8_t has_byte[256],
+                            uint16_t *output, size_t *m_out, size_t *num_syms_out,
+                            uint64_t freqs[258])
+{
+    uint16_t names[256];
+    memset(names, 0, sizeof names);
+    uint16_t num_names = 0;
+    for (size_t b = 0; b < 256; b++) {
+        if (has_byte[b]) { names[b] = num_names; num_names += 1; }
+    }
+    if (!(0 < num_names && num_names < 257)) orc_panic("mtf: num_names range");
+
+    uint16_t eob = (uint16_t)(num_names + 1);
+    memset(freqs, 0, 258 * sizeof(uint64_t));
+
+    uint16_t recency[256];
+    memset(recency, 0, sizeof recency);
+    for (uint16_t k = 0; k < num_names; k++) recency[k] = k;
+
+    size_t m = 0;
+    size_t zero_count = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint16_t i_name = names[buf[i]];
+        uint16_t primary = recency[0];
+        if (i_name == primary) {
+            zero_count += 1;
+        } else {
+            if (zero_count != 0) {
+                mtf_rle(output, &m, freqs, zero_count);
+                zero_count = 0;
+            }
+            uint16_t n0 = primary;
+            size_t r_i;
+            for (r_i = 1; r_i < 256; r_i++) {           /* mtf.rs:86-97 */
+                uint16_t t = recency[r_i];
+                recency[r_i] = n0;
+                n0 = t;
+                if (i_name == n0) {
+                    output[m++] = (uint16_t)(r_i + 1);
+                    freqs[r_i + 1] += 1;
+                    break;
+                }
+            }
+            recency[0] = i_name;
+        }
+    }
+    if (zero_count != 0) mtf_rle(output, &m, freqs, zero_count);
+
+    output[m++] = eob;                                  /* mtf.rs:112-113 */
+    freqs[eob] = 1;
+
+    *m_out = m;
+    *num_syms_out = (size_t)num_names + 2;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* lib/huffman.rs                                                           */
+/* ------------------------------------------------------------------------ */
+
+#define CODEWORD_MAX_LEN 17     /* huffman.rs:13  */
+#define INIT_LEN_HIGH 15        /* huffman.rs:303 */
+#define INIT_LEN_LOW 0          /* huffman.rs:304 */
+#define NUM_REFINEMENTS 4       /* huffman.rs:307 */
+#define SEGMENT_WIDTH 50        /* huffman.rs:310 */
+#define MAX_SYMS 258
+#define MAX_TABLES 6
+
+typedef struct { size_t w; uint8_t d; } Priority;     /* huffman.rs:144-145 */
+
+static inline int prio_lt(Priority a, Priority b)       /* derived PartialOrd: lexicographic */
+{
+    if (a.w != b.w) return a.w < b.w;
+    return a.d < b.d;
+}
+
+static inline Priority prio_add(Priority a, Priority b) /* huffman.rs:147-159 */
+{
+    Priority r;
+    r.w = a.w + b.w;
+    r.d = (uint8_t)((a.d > b.d ? a.d : b.d) + 1);
+    return r;
+}
+
+typedef struct { uint16_t sym; Priority p; } HeapItem;
+typedef struct { HeapItem heap[2 * MAX_SYMS]; size_t len; } FreqQueue;   /* 1-indexed access */
+
+#define ITEM(q, idx) ((q)->heap[(idx) - 1])
+
+/* huffman.rs:196-222 */
+static void fq_insert(FreqQueue *q, uint16_t sym, Priority pr)
+{
+    size_t init_idx = q->len + 1;
+    q->heap[q->len].sym = sym;
+    q->heap[q->len].p = pr;
+    q->len += 1;
+    if (init_idx == 1) return;
+
+    size_t this_idx = init_idx;
+    for (;;) {
+        size_t above_idx = this_idx >> 1;
+        HeapItem above = ITEM(q, above_idx);
+        if (prio_lt(pr, above.p)) {
+            ITEM(q, this_idx) = above;
+            this_idx = above_idx;
+            if (this_idx == 1) break;
+        } else {
+            break;
+        }
+    }
+    if (this_idx != init_idx) {
+        ITEM(q, this_idx).sym = sym;
+        ITEM(q, this_idx).p = pr;
+    }
+}
+
+/* huffman.rs:225-267 */
+static HeapItem fq_extract(FreqQueue *q)
+{
+    if (q->len == 0) orc_panic("Tried to extract() from empty heap");
+    HeapItem last = q->heap[q->len - 1];
+    q->len -= 1;
+    if (q->len == 0) return last;
+
+    HeapItem root = ITEM(q, 1);
+    ITEM(q, 1) = last;
+    size_t heap_size = q->len;
+
+    size_t this_idx = 1;
+    size_t final_idx;
+    for (;;) {
+        size_t left_idx = this_idx << 1;
+        if (left_idx > heap_size) { final_idx = this_idx; break; }
+        size_t right_idx = left_idx + 1;
+        size_t below_idx;
+        if (right_idx <= heap_size && prio_lt(ITEM(q, right_idx).p, ITEM(q, left_idx).p))
+            below_idx = right_idx;
+        else
+            below_idx = left_idx;
+        HeapItem below = ITEM(q, below_idx);
+        if (prio_lt(last.p, below.p)) { final_idx = this_idx; break; }
+        ITEM(q, this_idx) = below;
+        this_idx = below_idx;
+    }
+    ITEM(q, final_idx) = last;
+    return root;
+}
+
+/* huffman.rs:271-298 with Tree (:20-102) inlined as child arrays.
+ * Node 0 = root, leaves 1..=n, inner nodes n+1.. */
+ORC_API int orc_build_table(size_t num_syms, const uint64_t *freqs, uint8_t *lengths)
+{
+    if (num_syms < 2 || num_syms > MAX_SYMS) return -1;
+    size_t scaling = 1;
+    for (;;) {
+        int lchild[2 * MAX_SYMS], rchild[2 * MAX_SYMS];
+        size_t nodes_len = num_syms + 1;                 /* root + leaves */
+        for (size_t k = 0; k < 2 * MAX_SYMS; k++) { lchild[k] = -1; rchild[k] = -1; }
+
+        FreqQueue q;
+        q.len = 0;
+        for (size_t s = 0; s < num_syms; s++) {          /* huffman.rs:171-180 */
+            Priority p;
+            p.w = (size_t)(freqs[s] / scaling) + 1;
+            p.d = 0;
+            fq_insert(&q, (uint16_t)(s + 1), p);
+        }
+
+        for (;;) {
+            HeapItem one = fq_extract(&q);
+            HeapItem two = fq_extract(&q);
+            size_t parent;
+            if (nodes_len == num_syms * 2 - 1) {         /* Tree::tie :60-74 */
+                lchild[0] = one.sym;
+                rchild[0] = two.sym;
+                parent = 0;
+            } else {
+                parent = nodes_len;
+                lchild[parent] = one.sym;
+                rchild[parent] = two.sym;
+                nodes_len += 1;
+            }
+            if (parent == 0) break;
+            fq_insert(&q, (uint16_t)parent, prio_add(one.p, two.p));
+        }
+
+        /* coding_lengths :78-102 */
+        size_t max_len = 0;
+        size_t stack_id[2 * MAX_SYMS + 2], stack_len[2 * MAX_SYMS + 2];
+        size_t sp = 0;
+        stack_id[sp] = 0; stack_len[sp] = 0; sp++;
+        while (sp > 0) {
+            sp--;
+            size_t cur = stack_id[sp], len = stack_len[sp];
+            if (lchild[cur] >= 0 && rchild[cur] >= 0) {
+                stack_id[sp] = (size_t)lchild[cur]; stack_len[sp] = len + 1; sp++;
+                stack_id[sp] = (size_t)rchild[cur]; stack_len[sp] = len + 1; sp++;
+            } else {
+                if (cur == 0) orc_panic("unfinished tree");
+                lengths[cur - 1] = (uint8_t)len;
+                if (len > max_len) max_len = len;
+            }
+        }
+        if (max_len <= CODEWORD_MAX_LEN) return 0;
+        scaling <<= 1;
+    }
+}
+
+/* The modelling half of huffman::encode (huffman.rs:313-460): table count,
+ * initial tables, the four "refinement" iterations, selectors.
+ * tables: [MAX_TABLES][MAX_SYMS] code lengths; selectors: one byte per group. */
+static int huffman_model(const uint16_t *input, size_t input_size, size_t num_syms,
+                         const uint64_t *mtf_freqs, size_t *num_tables_out,
+                         uint8_t tables[MAX_TABLES][MAX_SYMS], uint8_t *selectors,
+                         size_t *num_selectors_out)
+{
+    size_t num_tables;
+    if (num_syms <= 2) orc_panic("Too few symbols for huffman::encode();");
+    else if (num_syms <= 199) num_tables = 2;
+    else if (num_syms <= 599) num_tables = 3;
+    else if (num_syms <= 1199) num_tables = 4;
+    else if (num_syms <= 2399) num_tables = 5;
+    else num_tables = 6;
+    if (num_syms > MAX_SYMS) orc_panic("num_syms > 258");
+
+    /* initial tables (:333-376) */
+    size_t freq_remaining = input_size;
+    size_t sym_left = 0;
+    for (size_t cur = 0; cur < num_tables; cur++) {
+        size_t tables_remaining = num_tables - cur;
+        size_t freq_target = freq_remaining / tables_remaining;
+        size_t freq_acc = 0;
+        size_t sym_right = sym_left;
+        for (;;) {
+            if (sym_right >= MAX_SYMS) orc_panic("mtf.freqs index out of range (SURVEY A-Q14)");
+            freq_acc += (size_t)mtf_freqs[sym_right];
+            if (freq_acc >= freq_target || (sym_right + 1) == num_syms) break;
+            sym_right += 1;
+        }
+        if (sym_right > sym_left && cur != 0 && cur != (num_tables - 1) && cur % 2 == 1) {
+            freq_acc -= (size_t)mtf_freqs[sym_right];
+            sym_right -= 1;
+        }
+        for (size_t s = 0; s < num_syms; s++)
+            tables[cur][s] = (s >= sym_left && s <= sym_right) ? INIT_LEN_HIGH : INIT_LEN_LOW;
+        sym_left = sym_right + 1;
+        freq_remaining -= freq_acc;
+    }
+
+    /* refinement (:389-460) */
+    /* table_freqs (:390-394): allocated once, never cleared between iterations */
+    uint64_t (*tf)[MAX_SYMS] = (uint64_t (*)[MAX_SYMS])xmalloc(sizeof(uint64_t) * MAX_TABLES * MAX_SYMS);
+    memset(tf, 0, sizeof(uint64_t) * MAX_TABLES * MAX_SYMS);
+    size_t nsel = 0;
+
+    for (int it = 0; it < NUM_REFINEMENTS; it++) {
+        int final_it = (it == NUM_REFINEMENTS - 1);
+        if (it != 0) {                                   /* :403-409 — zeroes `tables`, sic */
+            for (size_t t = 0; t < num_tables; t++)
+                for (size_t s = 0; s < num_syms; s++) tables[t][s] = 0;
+        }
+        size_t buf_left = 0;
+        for (;;) {
+            size_t buf_right = buf_left + SEGMENT_WIDTH - 1;
+            if (buf_right >= input_size) buf_right = input_size - 1;
+
+            size_t best_table = 0;
+            size_t best_cost = (size_t)-1;
+            for (size_t t = 0; t < num_tables; t++) {
+                size_t cost = 0;
+                for (size_t k = buf_left; k <= buf_right; k++) cost += tables[t][input[k]];
+                if (cost < best_cost) { best_table = t; best_cost = cost; }
+            }
+            for (size_t k = buf_left; k <= buf_right; k++) tf[best_table][input[k]] += 1;
+            if (final_it) selectors[nsel++] = (uint8_t)best_table;
+
+            buf_left = buf_right + 1;
+            if (buf_left >= input_size) break;
+        }
+        for (size_t t = 0; t < num_tables; t++) orc_build_table(num_syms, tf[t], tables[t]);
+    }
+    free(tf);
+    *num_tables_out = num_tables;
+    *num_selectors_out = nsel;
+    return 0;
+}
+
+/* The serialisation half of huffman::encode (huffman.rs:462-575) */
+static void huffman_write(BitWriter *out, const uint16_t *input, size_t input_size,
+                          size_t num_syms, size_t num_tables,
+                          uint8_t tables[MAX_TABLES][MAX_SYMS], const uint8_t *selectors,
+                          size_t num_selectors)
+{
+    bw_write_bits(out, (uint8_t)num_tables, 3);                 /* :465 */
+    bw_write_bits_u32(out, (uint32_t)num_selectors, 15);        /* :468-469 */
+
+    size_t selectors_mtf[MAX_TABLES];
+    uint8_t idx_codes[MAX_TABLES];
+    for (size_t i = 0; i < num_tables; i++) {
+        selectors_mtf[i] = i;
+        idx_codes[i] = (i == 0) ? 0 : (uint8_t)((1u << (i + 1)) - 2);
+    }
+    for (size_t k = 0; k < num_selectors; k++) {                /* :485-503 */
+        size_t sel = selectors[k];
+        size_t bump = selectors_mtf[0];
+        if (bump == sel) {
+            bw_write_bits(out, 0, 1);
+        } else {
+            size_t idx = 1;
+            for (;;) {
+                size_t stack_sel = selectors_mtf[idx];
+                selectors_mtf[idx] = bump;
+                if (stack_sel == sel) {
+                    bw_write_bits(out, idx_codes[idx], idx + 1);
+                    break;
+                }
+                bump = stack_sel;
+                idx += 1;
+            }
+            selectors_mtf[0] = sel;
+        }
+    }
+
+    uint32_t (*code_word)[MAX_SYMS] = (uint32_t (*)[MAX_SYMS])xmalloc(sizeof(uint32_t) * MAX_TABLES * MAX_SYMS);
+    size_t (*code_len)[MAX_SYMS] = (size_t (*)[MAX_SYMS])xmalloc(sizeof(size_t) * MAX_TABLES * MAX_SYMS);
+
+    for (size_t t = 0; t < num_tables; t++) {                   /* :509-562 */
+        const uint8_t *table = tables[t];
+        uint8_t min_len = 255, max_len = 0;
+        bw_write_bits(out, table[0], 5);
+        uint8_t acc = table[0];
+        for (size_t s = 0; s < num_syms; s++) {
+            uint8_t l = table[s];
+            for (;;) {
+                if (l == acc) { bw_write_bits(out, 0, 1); break; }
+                else if (l > acc) { bw_write_bits(out, 2, 2); acc += 1; }
+                else { bw_write_bits(out, 3, 2); acc -= 1; }
+            }
+            if (l < min_len) min_len = l;
+            if (l > max_len) max_len = l;
+        }
+        for (size_t s = 0; s < num_syms; s++) { code_len[t][s] = 0; code_word[t][s] = 0; }
+        uint32_t word = 0;
+        for (unsigned l = min_len; l <= max_len; l++) {
+            for (size_t s = 0; s < num_syms; s++) {
+                if (table[s] == l) {
+                    code_len[t][s] = l;
+                    code_word[t][s] = word;
+                    word += 1;
+                }
+            }
+            word <<= 1;
+        }
+    }
+
+    size_t sel = selectors[0];                                   /* :565-572 */
+    for (size_t i = 0; i < input_size; i++) {
+        if (i % 50 == 0) sel = selectors[i / 50];
+        bw_write_bits_u32(out, code_word[sel][input[i]], code_len[sel][input[i]]);
+    }
+    free(code_word);
+    free(code_len);
+}
+
+/* stage export: modelling only (tests compare the CUDA tables / selectors) */
+ORC_API int orc_huffman_model(const uint16_t *input, size_t input_size, size_t num_syms,
+                              const uint64_t *freqs, size_t *num_tables,
+                              uint8_t *tables_flat /* [6*258] */, uint8_t *selectors,
+                              size_t *num_selectors)
+{
+    uint8_t tables[MAX_TABLES][MAX_SYMS];
+    memset(tables, 0, sizeof tables);
+    int rc = huffman_model(input, input_size, num_syms, freqs, num_tables, tables, selectors,
+                           num_selectors);
+    memcpy(tables_flat, tables, sizeof tables);
+    return rc;
+}
+
+/* stage export: huffman::encode on a fresh, byte-aligned writer. Returns the
+ * number of BITS written; bytes (zero-padded) go to out if it fits. */
+ORC_API size_t orc_huffman_encode(const uint16_t *input, size_t input_size, size_t num_syms,
+                                  const uint64_t *freqs, uint8_t *out, size_t cap)
+{
+    uint8_t tables[MAX_TABLES][MAX_SYMS];
+    memset(tables, 0, sizeof tables);
+    uint8_t *selectors = (uint8_t *)xmalloc(input_size / SEGMENT_WIDTH + 2);
+    size_t nt = 0, ns = 0;
+    huffman_model(input, input_size, num_syms, freqs, &nt, tables, selectors, &ns);
+    BitWriter w;
+    bw_init(&w);
+    huffman_write(&w, input, input_size, num_syms, nt, tables, selectors, ns);
+    size_t bits = bw_bits(&w);
+    bw_close(&w);
+    if (out && w.len <= cap) memcpy(out, w.buf, w.len);
+    free(w.buf);
+    free(selectors);
+    return bits;
+}
+
+/* ------------------------------------------------------------------------ */
+/* lib/lib.rs — framing and the block loop                                  */
+/* ------------------------------------------------------------------------ */
+
+/* lib.rs:18-22 */
+static void write_stream_header(BitWriter *out, int level)
+{
+    uint8_t h[4] = { 0x42, 0x5A, 0x68, (uint8_t)('0' + level) };
+    bw_write_bytes(out, h, 4);
+}
+
+/* lib.rs:24-36 */
+static void write_block_header(BitWriter *out, uint32_t crc, size_t ptr)
+{
+    static const uint8_t magic[6] = { 0x31, 0x41, 0x59, 0x26, 0x53, 0x59 };
+    bw_write_bytes(out, magic, 6);
+    uint8_t c[4] = { (uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc };
+    bw_write_bytes(out, c, 4);
+    bw_write_bits(out, 0, 1);
+    uint8_t p[3] = { (uint8_t)(ptr >> 16), (uint8_t)(ptr >> 8), (uint8_t)ptr };
+    bw_write_bytes(out, p, 3);
+}
+
+/* lib.rs:39-64 */
+static void write_sym_map(BitWriter *out, const uint8_t *has_byte)
+{
+    uint16_t sector_map = 0;
+    uint16_t sectors[16];
+    size_t ns = 0;
+    for (unsigned a = 0; a < 16; a++) {
+        sector_map <<= 1;
+        uint16_t sector = 0;
+        for (unsigned b = 0; b < 16; b++) {
+            sector <<= 1;
+            if (has_byte[(a << 4) | b]) sector |= 1;
+        }
+        if (sector != 0) {
+            sector_map |= 1;
+            sectors[ns++] = sector;
+        }
+    }
+    if (ns == 0) orc_panic("write_sym_map: empty");
+    uint8_t be[2] = { (uint8_t)(sector_map >> 8), (uint8_t)sector_map };
+    bw_write_bytes(out, be, 2);
+    for (size_t k = 0; k < ns; k++) {
+        be[0] = (uint8_t)(sectors[k] >> 8);
+        be[1] = (uint8_t)sectors[k];
+        bw_write_bytes(out, be, 2);
+    }
+}
+
+/* lib.rs:66-70 */
+static void write_stream_footer(BitWriter *out, uint32_t crc)
+{
+    static const uint8_t magic[6] = { 0x17, 0x72, 0x45, 0x38, 0x50, 0x90 };
+    bw_write_bytes(out, magic, 6);
+    uint8_t c[4] = { (uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc };
+    bw_write_bytes(out, c, 4);
+}
+
+/* Per-block trace for stage-level parity tests (not in the reference). */
+typedef struct {
+    uint64_t in_off;      /* offset of the block's first input byte           */
+    uint64_t consumed;    /* input bytes consumed by this block (rle.rs:251)  */
+    uint64_t rle_len;     /* RLE1 output length n                             */
+    uint64_t mtf_len;     /* MTF/RLE2 symbol count m (incl. EOB)              */
+    uint64_t bit_off;     /* bit offset of the block magic in the stream      */
+    uint64_t bit_len;     /* bits from block magic through the last symbol    */
+    uint32_t crc;         /* block CRC                                        */
+    uint32_t ptr;         /* origPtr                                          */
+    uint32_t num_syms;
+    uint32_t num_tables;
+} OrcBlockInfo;
+
+/* lib.rs:84-132.  *out is malloc'ed (free with orc_free). If infos != NULL up
+ * to infos_cap block traces are recorded; *n_blocks gets the block count. */
+ORC_API int orc_encode_ex(const uint8_t *in, size_t n, int level, uint8_t **out, size_t *out_len,
+                          size_t *consumed_out, OrcBlockInfo *infos, size_t infos_cap,
+                          size_t *n_blocks)
+{
+    if (level < 1 || level > 9) return -1;           /* the reference panics (lib.rs:89) */
+    BitWriter w;
+    bw_init(&w);
+    write_stream_header(&w, level);
+
+    uint32_t stream_crc = 0;
+    size_t consumed = 0;
+    size_t nb = 0;
+    size_t cap = (size_t)100000 * (size_t)level;
+    uint8_t *rle_buf = (uint8_t *)xmalloc(cap);
+    uint8_t *bwt_buf = (uint8_t *)xmalloc(cap);
+    uint16_t *mtf_buf = (uint16_t *)xmalloc((cap + 1) * sizeof(uint16_t));
+    uint8_t *selectors = (uint8_t *)xmalloc(cap / SEGMENT_WIDTH + 2);
+
+    for (;;) {
+        size_t rle_len = 0, took = 0;
+        uint32_t chk = 0;
+        orc_rle_one(in + consumed, n - consumed, level, rle_buf, &rle_len, &took, &chk);
+        if (took == 0) break;                                          /* lib.rs:103-105 */
+
+        stream_crc = chk ^ ((stream_crc << 1) | (stream_crc >> 31));   /* lib.rs:108 */
+
+        uint32_t ptr = 0;
+        uint8_t has_byte[256];
+        orc_bwt(rle_buf, rle_len, bwt_buf, &ptr, has_byte);
+
+        size_t bit0 = bw_bits(&w);
+        write_block_header(&w, chk, ptr);
+        write_sym_map(&w, has_byte);
+
+        size_t m = 0, num_syms = 0;
+        uint64_t freqs[258];
+        orc_mtf_and_rle(bwt_buf, rle_len, has_byte, mtf_buf, &m, &num_syms, freqs);
+
+        uint8_t tables[MAX_TABLES][MAX_SYMS];
+        memset(tables, 0, sizeof tables);
+        size_t nt = 0, ns = 0;
+        huffman_model(mtf_buf, m, num_syms, freqs, &nt, tables, selectors, &ns);
+        huffman_write(&w, mtf_buf, m, num_syms, nt, tables, selectors, ns);
+
+        if (infos && nb < infos_cap) {
+            OrcBlockInfo *bi = &infos[nb];
+            bi->in_off = consumed;
+            bi->consumed = took;
+            bi->rle_len = rle_len;
+            bi->mtf_len = m;
+            bi->bit_off = bit0;
+            bi->bit_len = bw_bits(&w) - bit0;
+            bi->crc = chk;
+            bi->ptr = ptr;
+            bi->num_syms = (uint32_t)num_syms;
+            bi->num_tables = (uint32_t)nt;
+        }
+        nb += 1;
+        consumed += took;
+        if (consumed >= n) break;            /* lib.rs:122-125 with a true EOF test (A-Q4) */
+    }
+
+    write_stream_footer(&w, stream_crc);
+    bw_close(&w);
+
+    free(rle_buf);
+    free(bwt_buf);
+    free(mtf_buf);
+    free(selectors);
+    *out = w.buf;
+    *out_len = w.len;
+    if (consumed_out) *consumed_out = consumed;
+    if (n_blocks) *n_blocks = nb;
+    return 0;
+}
+
+ORC_API int orc_encode(const uint8_t *in, size_t n, int level, uint8_t **out, size_t *out_len,
+                       size_t *consumed_out)
+{
+    return orc_encode_ex(in, n, level, out, out_len, consumed_out, NULL, 0, NULL);
+}
+
+ORC_API void orc_free(void *p) { free(p); }
