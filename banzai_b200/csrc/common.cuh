@@ -1,0 +1,121 @@
+// common.cuh — shared device/host helpers for the banzai_b200 CUDA kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+namespace bnz {
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ u32 warp_id() { return threadIdx.x >> 5; }
+__device__ __forceinline__ u32 lanemask_lt()
+{
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// inclusive warp scans
+__device__ __forceinline__ u32 warp_incl_sum(u32 v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= (u32)d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ u32 warp_incl_max(u32 v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= (u32)d) v = max(v, t);
+    }
+    return v;
+}
+__device__ __forceinline__ u64 warp_incl_sum64(u64 v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= (u32)d) v += t;
+    }
+    return v;
+}
+
+// Block-wide exclusive sum scan of one value per thread. `scratch` holds >= 33 words.
+// Returns the exclusive prefix; *total gets the block sum. Ends with a barrier so
+// scratch can be reused immediately.
+template <int NT>
+__device__ __forceinline__ u32 block_excl_sum(u32 v, u32 *scratch, u32 *total)
+{
+    constexpr int NWARP = NT / 32;
+    u32 inc = warp_incl_sum(v);
+    if (lane_id() == 31) scratch[warp_id()] = inc;
+    __syncthreads();
+    if (warp_id() == 0) {
+        u32 w = lane_id() < NWARP ? scratch[lane_id()] : 0;
+        u32 wi = warp_incl_sum(w);
+        scratch[lane_id()] = wi - w;
+        if (lane_id() == 31) scratch[32] = wi;
+    }
+    __syncthreads();
+    u32 res = scratch[warp_id()] + inc - v;
+    *total = scratch[32];
+    __syncthreads();
+    return res;
+}
+
+// Block-wide EXCLUSIVE max scan (one value per thread; identity 0), same scratch contract.
+template <int NT>
+__device__ __forceinline__ u32 block_excl_max(u32 v, u32 *scratch, u32 *total)
+{
+    constexpr int NWARP = NT / 32;
+    u32 inc = warp_incl_max(v);
+    u32 ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane_id() == 0) ex = 0;
+    if (lane_id() == 31) scratch[warp_id()] = inc;
+    __syncthreads();
+    if (warp_id() == 0) {
+        u32 w = lane_id() < NWARP ? scratch[lane_id()] : 0;
+        u32 wi = warp_incl_max(w);
+        u32 wex = __shfl_up_sync(0xffffffffu, wi, 1);
+        if (lane_id() == 0) wex = 0;
+        scratch[lane_id()] = wex;
+        if (lane_id() == 31) scratch[32] = wi;
+    }
+    __syncthreads();
+    u32 res = max(scratch[warp_id()], ex);
+    *total = scratch[32];
+    __syncthreads();
+    return res;
+}
+
+template <int NT>
+__device__ __forceinline__ u32 block_sum(u32 v, u32 *scratch)
+{
+    constexpr int NWARP = NT / 32;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (lane_id() == 0) scratch[warp_id()] = v;
+    __syncthreads();
+    u32 r = 0;
+    if (warp_id() == 0) {
+        u32 w = lane_id() < NWARP ? scratch[lane_id()] : 0;
+        w = __reduce_add_sync(0xffffffffu, w);
+        if (lane_id() == 0) scratch[32] = w;
+    }
+    __syncthreads();
+    r = scratch[32];
+    __syncthreads();
+    return r;
+}
+
+}  // namespace bnz

@@ -1,0 +1,162 @@
+/* banzai_b200.h — C ABI of the B200-native bzip2 encoder core.
+ *
+ * Drop-in boundary for the block-compression path of jgbyrne/banzai v0.3.1.  Every entry
+ * point cites the reference interface it replaces (paths relative to the reference repo).
+ * Plain pointers and sizes only; no C++/torch types.  The library fails loudly
+ * (BNZ_ECUDA) when no CUDA device / sm_100a kernel image is usable: there is no CPU
+ * fallback.
+ *
+ * Threading: a bnz_ctx is not thread-safe; use one per host thread.
+ */
+#ifndef BANZAI_B200_H
+#define BANZAI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BNZ_API __attribute__((visibility("default")))
+#else
+#define BNZ_API
+#endif
+
+typedef struct bnz_ctx bnz_ctx;
+
+enum {
+    BNZ_OK = 0,
+    BNZ_EINVAL = 1,     /* bad argument; level outside 1..=9 (the reference panics: lib/lib.rs:19,89) */
+    BNZ_ECUDA = 2,      /* CUDA runtime / driver error, or no usable device */
+    BNZ_ENOMEM = 3,     /* host or device allocation failed */
+    BNZ_EINTERNAL = 4   /* internal invariant violated (reference: assert!/panic! sites) */
+};
+
+/* ---- context -------------------------------------------------------------------------
+ * The reference has no context (single-threaded, lib/lib.rs:84); the context owns what a
+ * GPU path needs across calls: per-device streams, device arenas, pinned staging. */
+
+/* n_gpus: number of visible CUDA devices to shard blocks over (0 = all visible). */
+BNZ_API int bnz_ctx_create(bnz_ctx **out, int n_gpus);
+/* explicit device ordinals (e.g. {LOCAL_RANK} for one-process-per-GPU launches) */
+BNZ_API int bnz_ctx_create_on(bnz_ctx **out, const int *device_ids, int n_devices);
+BNZ_API void bnz_ctx_destroy(bnz_ctx *ctx);
+BNZ_API const char *bnz_strerror(int code);
+/* human-readable detail of the last failing call on this context ("" if none) */
+BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
+
+/* tunables (call before encoding). key: "bwt_radix_bits" (8|10), "bwt_ctas_per_sm" (0=auto) */
+BNZ_API int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value);
+
+/* ---- the hot path --------------------------------------------------------------------
+ * Replaces `banzai::encode(reader, BufWriter, level) -> io::Result<usize>`
+ * (lib/lib.rs:84-132) on a whole in-memory input: the caller's shim does
+ * read_to_end -> bnz_encode -> write_all -> flush.
+ *   in/in_len : input bytes in HOST memory (pinned memory from bnz_host_alloc is fastest)
+ *   level     : 1..=9, block size = level * 100 000 (lib/rle.rs:121)
+ *   *out      : complete .bz2 stream, byte-identical to the reference's; allocated by the
+ *               library, release with bnz_free
+ *   *consumed : input bytes encoded (== in_len on success; lib/lib.rs:119,131)
+ */
+BNZ_API int bnz_encode(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int level,
+                       uint8_t **out, size_t *out_len, size_t *consumed);
+BNZ_API void bnz_free(bnz_ctx *ctx, uint8_t *p);
+
+/* Same computation with the input already resident in device memory of the context's
+ * first device and the stream left on the device (used to time the kernels without
+ * PCIe).  d_out must hold bnz_max_compressed_size(in_len) bytes. */
+BNZ_API int bnz_encode_device(bnz_ctx *ctx, const void *d_in, size_t in_len, int level,
+                              void *d_out, size_t d_out_cap, size_t *out_len);
+BNZ_API size_t bnz_max_compressed_size(size_t in_len);
+
+/* `banzai::encode_file(in_path, out_path)` (lib/lib.rs:141-153): level 9, returns bytes
+ * encoded through *consumed. */
+BNZ_API int bnz_encode_file(bnz_ctx *ctx, const char *in_path, const char *out_path,
+                            size_t *consumed);
+
+/* pinned host buffers for inputs (H2D at full PCIe rate) */
+BNZ_API void *bnz_host_alloc(size_t bytes);
+BNZ_API void bnz_host_free(void *p);
+/* raw device buffers on the context's first device (for bnz_encode_device callers) */
+BNZ_API void *bnz_device_alloc(bnz_ctx *ctx, size_t bytes);
+BNZ_API void bnz_device_free(bnz_ctx *ctx, void *p);
+BNZ_API int bnz_memcpy_h2d(bnz_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+BNZ_API int bnz_memcpy_d2h(bnz_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+
+/* ---- measurement ----------------------------------------------------------------------
+ * Filled by the last bnz_encode / bnz_encode_device on this context.  Times are CUDA-event
+ * milliseconds on the library's own stream of device 0 (max over devices for *_ms_max). */
+typedef struct bnz_stats {
+    uint64_t in_bytes, out_bytes;
+    uint32_t n_blocks;
+    uint32_t n_devices;
+    uint32_t kernel_launches;        /* kernels launched by this library during the call */
+    uint32_t bwt_radix_bits;
+    float total_ms;                  /* first kernel/copy -> last, device 0 */
+    float h2d_ms, d2h_ms;
+    float rle_ms, crc_ms, bwt_ms, mtf_ms, huff_ms, pack_ms;
+    /* BWT sort accounting: sum over blocks */
+    uint64_t bwt_n;                  /* sum of n */
+    uint64_t bwt_sum_active;         /* sum over blocks/rounds of records sorted */
+    uint64_t bwt_sum_active_passes;  /* sum of records sorted x radix passes executed */
+    uint32_t bwt_max_rounds;
+    uint32_t bwt_tied_blocks;
+    uint64_t bwt_rounds_total;
+    uint64_t bwt_algorithmic_bytes;  /* n + 8n + sum a_r * (16 P_r + 36)   */
+    uint64_t h2d_bytes, d2h_bytes;
+} bnz_stats;
+BNZ_API int bnz_get_stats(const bnz_ctx *ctx, bnz_stats *out);
+
+/* ---- stage-level exports (parity seams; mirror the reference's private stage fns) -----
+ * All take HOST buffers describing a batch of independent blocks and run only the named
+ * kernels on the context's first device.
+ */
+
+/* `rle::rle_one` applied repeatedly as `encode` does (lib/rle.rs:102, lib/lib.rs:101-126):
+ * block cuts, RLE1 bytes and block CRCs for a whole input.
+ *   blk_in_off[b], blk_in_len[b]  : consumed input range of block b
+ *   blk_rle_off[b], blk_rle_len[b]: its RLE1 image inside rle_out (concatenated)
+ *   blk_crc[b]                    : CRC-32/BZIP2 of the consumed input (lib/crc32.rs:31)
+ * Capacity: max_blocks entries / rle_cap bytes; *n_blocks returns the count. */
+BNZ_API int bnz_stage_rle1(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int level,
+                           uint64_t *blk_in_off, uint64_t *blk_in_len, uint64_t *blk_rle_off,
+                           uint32_t *blk_rle_len, uint32_t *blk_crc, size_t max_blocks,
+                           uint8_t *rle_out, size_t rle_cap, size_t *n_blocks);
+
+/* `bwt::bwt` (lib/bwt.rs:526) on n_blocks independent blocks stored back to back:
+ * block b = blocks[blk_off[b] .. blk_off[b] + blk_len[b]).  Outputs use the same layout.
+ * has_byte is [n_blocks][256]. max block length = 100000*level. */
+typedef struct bnz_bwt_block_stats {
+    uint32_t n, rounds, tied, pad;
+    uint64_t sum_active, sum_active_passes;
+} bnz_bwt_block_stats;
+BNZ_API int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t *blk_off,
+                          const uint32_t *blk_len, size_t n_blocks, int level, uint8_t *bwt_out,
+                          uint32_t *ptr_out, uint8_t *has_byte_out,
+                          bnz_bwt_block_stats *stats_out /* may be NULL */);
+
+/* `mtf::mtf_and_rle` (lib/mtf.rs:14) on a batch of BWT blocks (same layout as above).
+ * syms_out: u16 symbols of block b at syms_out + sym_off[b] where sym_off[b] = blk_off[b] + b
+ * (each block may emit up to n+1 symbols); sym_len[b] = m; num_syms[b]; freqs [n_blocks][258]. */
+BNZ_API int bnz_stage_mtf(bnz_ctx *ctx, const uint8_t *bwt, const uint64_t *blk_off,
+                          const uint32_t *blk_len, const uint8_t *has_byte, size_t n_blocks,
+                          uint16_t *syms_out, uint32_t *sym_len, uint32_t *num_syms,
+                          uint32_t *freqs_out);
+
+/* `huffman::encode` (lib/huffman.rs:313) on a batch of MTF blocks: block b's symbols at
+ * syms + sym_off[b], length sym_len[b].  Emits, per block, the bits huffman::encode writes
+ * to a fresh byte-aligned writer: bits_out + bit_byte_off[b] (zero padded), bit_len[b] bits.
+ * tables_out [n_blocks][6][258] code lengths, num_tables[b]; selectors are all in the stream.
+ * Per-block output capacity = out_stride bytes. */
+BNZ_API int bnz_stage_huffman(bnz_ctx *ctx, const uint16_t *syms, const uint64_t *sym_off,
+                              const uint32_t *sym_len, const uint32_t *num_syms,
+                              const uint32_t *freqs, size_t n_blocks, uint8_t *bits_out,
+                              size_t out_stride, uint64_t *bit_len, uint8_t *tables_out,
+                              uint32_t *num_tables);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BANZAI_B200_H */

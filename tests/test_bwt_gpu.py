@@ -1,0 +1,86 @@
+"""GPU parity: K3/K4 BWT rotation sort vs the oracle's `bwt::bwt` (reference lib/bwt.rs:526).
+Bit-exact: BWT bytes, origPtr and has_byte must all match."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import corpus
+from oracle import pyoracle as O
+
+pytestmark = pytest.mark.gpu
+
+KATS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import banzai_b200
+    c = banzai_b200.Context(n_gpus=1)
+    yield c
+    c.close()
+
+
+def _check(ctx, blocks, level=9, bits=(8, 10)):
+    for b in bits:
+        ctx.set("bwt_radix_bits", b)
+        got = ctx.stage_bwt(blocks, level, with_stats=True)
+        for blk, (bw, ptr, has, st) in zip(blocks, got):
+            ebw, eptr, ehas = O.bwt(blk)
+            assert ptr == eptr, (len(blk), st)
+            assert bytes(bw) == bytes(ebw), (len(blk), st)
+            assert (has == ehas).all()
+    return got
+
+
+def test_reference_kat_sentence(ctx):
+    k = KATS["bwt_smoke"]
+    got = _check(ctx, [k["input"].encode()])
+    assert bytes(got[0][0]).decode() == k["bwt"] and got[0][1] == k["ptr"]
+
+
+def test_tiny_and_edge_lengths(ctx):
+    blocks = [b"x", b"aa", b"ab", b"ba", b"aaa", b"abc", b"abab", b"aaaa", b"abcab", b"abcabc",
+              bytes(10), b"ab" * 7, b"ba" * 7, b"abcdefg" * 1000, bytes(range(256))]
+    _check(ctx, blocks, level=1)
+
+
+def test_random_small_alphabets(ctx):
+    rng = np.random.default_rng(5)
+    blocks = []
+    for _ in range(200):
+        n = int(rng.integers(1, 3000))
+        sigma = int(rng.integers(1, 5))
+        blocks.append(rng.integers(0, sigma, n).astype(np.uint8).tobytes())
+    _check(ctx, blocks, level=1)
+
+
+def test_periodic_equal_rotations_and_deep_doubling(ctx):
+    unit = corpus.random_bytes(1000, seed=corpus.SEED_C3).tobytes()
+    blocks = [
+        b"abcdefg" * 1000,                       # period | n  -> equal rotations (V7: ptr 999)
+        unit * 100,                              # period 1000 | 100000
+        (b"ab" * 50000)[:99999],                 # period 2 does not divide n -> deep doubling
+        (b"abcdefg" * 15000)[:99999],
+        (unit * 100)[:99999],
+        bytes(99999),                            # one symbol
+        b"\x00\x00\x00\x00\xfb" * 19999 + b"\x00\x00\x00",   # what RLE1 makes of zeros
+    ]
+    got = _check(ctx, blocks, level=1)
+    assert got[0][1] == 999
+    assert got[0][3]["tied"] == 1 and got[1][3]["tied"] == 1
+    assert got[2][3]["tied"] == 0
+
+
+@pytest.mark.parametrize("kind", ["text", "source", "binary", "random"])
+def test_full_blocks_level9(ctx, kind):
+    data = corpus.by_name(kind, 2 * 899999 + 12345)
+    blocks = [data[:899999].tobytes(), data[899999:2 * 899999].tobytes(), data[2 * 899999:].tobytes()]
+    _check(ctx, blocks, level=9, bits=(8,) if kind != "text" else (8, 10))
+
+
+def test_many_blocks_more_than_ctas(ctx):
+    data = corpus.mixed(700 * 20000)
+    blocks = [data[i * 20000:(i + 1) * 20000].tobytes() for i in range(700)]
+    _check(ctx, blocks, level=1, bits=(8,))
