@@ -59,7 +59,7 @@ lib.bnz_ctx_set.argtypes = [_vp, C.c_char_p, C.c_long]
 lib.bnz_encode.argtypes = [_vp, _vp, _sz, C.c_int, C.POINTER(_vp), _szp, _szp]
 lib.bnz_free.argtypes = [_vp, _vp]
 lib.bnz_free.restype = None
-lib.bnz_encode_device.argtypes = [_vp, _vp, _sz, C.c_int, _vp, _sz, _szp]
+lib.bnz_encode_device.argtypes = [_vp, _vp, _vp, _sz, C.c_int, _vp, _sz, _szp]
 lib.bnz_max_compressed_size.argtypes = [_sz]
 lib.bnz_max_compressed_size.restype = _sz
 lib.bnz_encode_file.argtypes = [_vp, C.c_char_p, C.c_char_p, _szp]

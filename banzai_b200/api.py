@@ -99,9 +99,10 @@ class Context:
     def free_out(self, out):
         lib.bnz_free(self._h, out)
 
-    def encode_device(self, d_in, n, level, d_out, d_out_cap):
+    def encode_device(self, d_in, h_in, n, level, d_out, d_out_cap):
         olen = C.c_size_t()
-        self._check(lib.bnz_encode_device(self._h, d_in, n, level, d_out, d_out_cap, C.byref(olen)))
+        self._check(lib.bnz_encode_device(self._h, d_in, h_in, n, level, d_out, d_out_cap,
+                                          C.byref(olen)))
         return olen.value
 
     # ---- stage seams ----------------------------------------------------------------

@@ -4,8 +4,38 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <vector>
+
+#define RLE_CHUNK 1024
+#define MTF_SEG 1024
+#define HUFF_MAX_SYMS 258
+#define HUFF_MAX_TABLES 6
+#define HUFF_REFINEMENTS 4        /* huffman.rs:307 */
 
 namespace bnz {
+
+// ---------------------------------------------------------------- K1/K2 RLE1 + CRC (rle1.cu)
+
+struct RleBlock {                 // one bzip2 block as cut by the host walk
+    uint64_t s;                   // first input byte
+    uint64_t c;                   // one past the last consumed input byte
+    uint64_t e0;                  // end of the (possibly truncated) run the block starts in, <= c
+    uint64_t P_e0;                // cost prefix P at e0
+    uint64_t rle_off;             // offset of the block's RLE1 image in the rle buffer
+    uint32_t u0;                  // output bytes of the first run: g(e0 - s)
+    uint32_t n;                   // RLE1 length of the block
+};
+
+cudaError_t crc_upload_tables();
+uint32_t crc_finalize(uint32_t acc, uint64_t len);
+cudaError_t rle_summary_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks, uint64_t *d_lasthead,
+                               uint32_t *d_meta, uint32_t *d_restsum, uint64_t *d_oin, uint64_t *d_P,
+                               cudaStream_t st);
+cudaError_t rle_emit_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks, const uint64_t *d_oin,
+                            const uint64_t *d_P, const RleBlock *d_blocks, uint32_t n_blocks, uint8_t *d_out,
+                            uint32_t *d_crc_acc, cudaStream_t st);
+int rle_walk_cuts(const uint8_t *in, uint64_t N, int level, const uint64_t *P, const uint64_t *o_in,
+                  uint64_t n_chunks, std::vector<RleBlock> &blocks);
 
 // ---------------------------------------------------------------- K3/K4 BWT (bwt_sort.cu)
 
@@ -37,5 +67,62 @@ size_t bwt_smem_bytes(int bits);
 int bwt_passes(int bits);
 cudaError_t bwt_max_ctas(int bits, int *ctas_per_sm);
 cudaError_t bwt_launch(const BwtArgs &a, int bits, int grid, cudaStream_t stream);
+
+// ---------------------------------------------------------------- K5 MTF + RLE2 (mtf.cu)
+
+struct MtfArgs {
+    const uint8_t *bwt;           // BWT bytes of all blocks (block b at bwt + blk_off[b])
+    uint8_t *idx;                 // scratch: one MTF index byte per position, same layout
+    const uint64_t *blk_off;      // [n_blocks]
+    const uint32_t *blk_len;      // [n_blocks]
+    const uint8_t *has_byte;      // [n_blocks][256]
+    uint32_t n_blocks;
+    const uint32_t *seg_base;     // [n_blocks + 1] first global segment of each block
+    uint32_t total_segs;
+    uint8_t *seg_list;            // [total_segs][256] distinct bytes, newest first
+    uint32_t *seg_cnt;            // [total_segs]
+    uint8_t *seg_state;           // [total_segs][256] recency list at the segment start
+    uint32_t *num_names;          // [n_blocks] out
+    uint16_t *syms;               // symbols out (block b at syms + sym_off[b])
+    const uint64_t *sym_off;      // [n_blocks] element offsets, room for blk_len + 1 each
+    uint32_t *sym_len;            // [n_blocks] out: m (incl. EOB)
+    uint32_t *freqs;              // [n_blocks][258] out
+};
+cudaError_t mtf_launch(const MtfArgs &a, cudaStream_t st, uint32_t *launches);
+
+// ---------------------------------------------------------------- K6-K8 Huffman + packing (huffman.cu)
+
+struct HuffArgs {
+    const uint16_t *syms;         // MTF symbols (block b at syms + sym_off[b])
+    const uint64_t *sym_off;      // [n_blocks]
+    const uint32_t *sym_len;      // [n_blocks] m
+    const uint32_t *num_names;    // [n_blocks]; num_syms = num_names + 2
+    const uint32_t *freqs;        // [n_blocks][258]
+    uint32_t n_blocks;
+    uint8_t *lens;                // [n_blocks][6][258] code lengths (initial tables, then final)
+    uint32_t *codes;              // [n_blocks][6][258] (len << 24) | code
+    uint32_t *tf;                 // [n_blocks][6][258] table_freqs (zeroed by the host)
+    uint32_t *num_tables;         // [n_blocks]
+    uint32_t *num_sel;            // [n_blocks]
+    const uint8_t *selectors;     // nullptr: every selector is 0 (SURVEY A-Q10)
+    size_t sel_stride;
+    const uint32_t *span_base;    // [n_blocks + 1] first assign-CTA of each block
+    uint32_t *hdr;                // [n_blocks][hdr_stride] header bits as MSB-first words
+    size_t hdr_stride;
+    uint32_t *hdr_bits;           // [n_blocks]
+    int with_block_header;        // 1: magic/crc/ptr/symmap precede the huffman part
+    const uint32_t *crc;          // [n_blocks]
+    const uint32_t *ptr;          // [n_blocks]
+    const uint8_t *has_byte;      // [n_blocks][256]
+    uint64_t *blk_bits;           // [n_blocks] bits of each block
+    uint64_t *blk_bitoff;         // [n_blocks] bit offset of each block in out_words
+    uint64_t bit_base;            // bit offset of the first block
+    uint64_t fixed_stride_bits;   // != 0: block b starts at b * fixed_stride_bits (stage tests)
+    uint64_t *total_bits;         // bit_base + sum of blk_bits
+    uint32_t *out_words;          // output stream (zeroed by the host)
+};
+cudaError_t huff_launch(const HuffArgs &a, uint32_t total_spans, cudaStream_t st, uint32_t *launches);
+cudaError_t huff_pack_launch(const HuffArgs &a, cudaStream_t st, uint32_t *launches);
+uint32_t huff_groups_per_span();
 
 }  // namespace bnz

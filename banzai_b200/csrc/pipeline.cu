@@ -49,6 +49,12 @@ struct Device {
     cudaStream_t stream = nullptr;
     // arenas (grown on demand, kept across calls)
     DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank;
+    DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, rle_blocks, crc_acc;
+    DevBuf seg_base, seg_list, seg_cnt, seg_state, num_names, syms, sym_off, sym_len, freqs;
+    DevBuf lens, codes, tf, num_tables, num_sel, span_base, hdr, hdr_bits, crc, blk_bits, blk_bitoff,
+        total_bits, out;
+    cudaEvent_t ev[12] = {};
+    bool crc_tables = false;
     uint32_t launches = 0;
 };
 
@@ -58,6 +64,10 @@ struct bnz_ctx {
     bnz_stats stats;
     int radix_bits = 8;
     int ctas_per_sm = 0;
+    // cached pinned output buffer handed to the caller by bnz_encode / returned by bnz_free
+    uint8_t *out_cache = nullptr;
+    size_t out_cache_cap = 0;
+    bool out_cache_lent = false;
 };
 
 #define CK(ctx, call)                                                                          \
@@ -115,6 +125,11 @@ extern "C" int bnz_ctx_create_on(bnz_ctx **out, const int *device_ids, int n_dev
             return BNZ_ECUDA;
         }
         d.sm_count = prop.multiProcessorCount;
+        for (cudaEvent_t &e : d.ev)
+            if (cudaEventCreate(&e) != cudaSuccess) {
+                delete ctx;
+                return BNZ_ECUDA;
+            }
         ctx->devs.push_back(d);
     }
     *out = ctx;
@@ -139,10 +154,18 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
         cudaSetDevice(d.id);
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (DevBuf *b : { &d.in, &d.rle, &d.bwt, &d.blk_off, &d.blk_len, &d.ptr, &d.has_byte,
-                           &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank })
+                           &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ch_lasthead, &d.ch_meta,
+                           &d.ch_restsum, &d.ch_oin, &d.ch_P, &d.rle_blocks, &d.crc_acc, &d.seg_base,
+                           &d.seg_list, &d.seg_cnt, &d.seg_state, &d.num_names, &d.syms, &d.sym_off,
+                           &d.sym_len, &d.freqs, &d.lens, &d.codes, &d.tf, &d.num_tables, &d.num_sel,
+                           &d.span_base, &d.hdr, &d.hdr_bits, &d.crc, &d.blk_bits, &d.blk_bitoff,
+                           &d.total_bits, &d.out })
             b->release();
+        for (cudaEvent_t e : d.ev)
+            if (e) cudaEventDestroy(e);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
+    if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
     delete ctx;
 }
 
@@ -331,35 +354,608 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
 }
 
 // ---------------------------------------------------------------------------------------
-// not yet implemented entry points (filled in by later milestones)
+// RLE1 + cuts + CRC on one device.  d_in: device copy of the input, h_in: host copy (the cut
+// walk reads <= 2 KiB of it per block).  Leaves the RLE1 images in d.rle and fills `blocks`
+// and `crcs`.
 // ---------------------------------------------------------------------------------------
 
-extern "C" int bnz_encode(bnz_ctx *ctx, const uint8_t *, size_t, int, uint8_t **, size_t *, size_t *)
+struct HostScratch {
+    std::vector<uint64_t> P, oin;
+    std::vector<uint32_t> acc;
+};
+
+static int run_rle_device(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const uint8_t *h_in, uint64_t N,
+                          int level, std::vector<RleBlock> &blocks, std::vector<uint32_t> &crcs,
+                          uint64_t *rle_total)
 {
-    return fail(ctx, BNZ_EINTERNAL, "bnz_encode: not implemented yet");
+    blocks.clear();
+    crcs.clear();
+    *rle_total = 0;
+    if (N == 0) return BNZ_OK;
+    if (!d.crc_tables) {
+        CK(ctx, crc_upload_tables());
+        d.crc_tables = true;
+    }
+    const uint64_t n_chunks = (N + RLE_CHUNK - 1) / RLE_CHUNK;
+    CK(ctx, d.ch_lasthead.ensure(n_chunks * 8));
+    CK(ctx, d.ch_meta.ensure(n_chunks * 4));
+    CK(ctx, d.ch_restsum.ensure(n_chunks * 4));
+    CK(ctx, d.ch_oin.ensure(n_chunks * 8));
+    CK(ctx, d.ch_P.ensure((n_chunks + 1) * 8));
+    CK(ctx, rle_summary_launch(d_in, N, n_chunks, d.ch_lasthead.as<uint64_t>(), d.ch_meta.as<uint32_t>(),
+                               d.ch_restsum.as<uint32_t>(), d.ch_oin.as<uint64_t>(), d.ch_P.as<uint64_t>(),
+                               d.stream));
+    d.launches += 2;
+    HostScratch hs;
+    hs.P.resize(n_chunks + 1);
+    hs.oin.resize(n_chunks);
+    CK(ctx, cudaMemcpyAsync(hs.P.data(), d.ch_P.p, (n_chunks + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaMemcpyAsync(hs.oin.data(), d.ch_oin.p, n_chunks * 8, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+
+    if (rle_walk_cuts(h_in, N, level, hs.P.data(), hs.oin.data(), n_chunks, blocks) != 0)
+        return fail(ctx, BNZ_EINTERNAL, "RLE1 cut walk failed");
+    const size_t nb = blocks.size();
+    uint64_t total = blocks.back().rle_off + ((blocks.back().n + 15) & ~15ull);
+    *rle_total = total;
+    CK(ctx, d.rle_blocks.ensure(nb * sizeof(RleBlock)));
+    CK(ctx, d.crc_acc.ensure(nb * 4));
+    CK(ctx, d.rle.ensure(total));
+    CK(ctx, cudaMemcpyAsync(d.rle_blocks.p, blocks.data(), nb * sizeof(RleBlock), cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemsetAsync(d.crc_acc.p, 0, nb * 4, d.stream));
+    CK(ctx, rle_emit_launch(d_in, N, n_chunks, d.ch_oin.as<uint64_t>(), d.ch_P.as<uint64_t>(),
+                            d.rle_blocks.as<RleBlock>(), (uint32_t)nb, d.rle.as<uint8_t>(),
+                            d.crc_acc.as<uint32_t>(), d.stream));
+    d.launches += 2;
+    hs.acc.resize(nb);
+    CK(ctx, cudaMemcpyAsync(hs.acc.data(), d.crc_acc.p, nb * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    crcs.resize(nb);
+    for (size_t b = 0; b < nb; b++) crcs[b] = crc_finalize(hs.acc[b], blocks[b].c - blocks[b].s);
+    return BNZ_OK;
 }
-extern "C" void bnz_free(bnz_ctx *, uint8_t *p) { free(p); }
-extern "C" int bnz_encode_device(bnz_ctx *ctx, const void *, size_t, int, void *, size_t, size_t *)
+
+extern "C" int bnz_stage_rle1(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int level, uint64_t *blk_in_off,
+                              uint64_t *blk_in_len, uint64_t *blk_rle_off, uint32_t *blk_rle_len,
+                              uint32_t *blk_crc, size_t max_blocks, uint8_t *rle_out, size_t rle_cap,
+                              size_t *n_blocks)
 {
-    return fail(ctx, BNZ_EINTERNAL, "bnz_encode_device: not implemented yet");
+    if (!ctx || level < 1 || level > 9 || !n_blocks) return BNZ_EINVAL;
+    *n_blocks = 0;
+    if (in_len == 0) return BNZ_OK;
+    Device &d = ctx->devs[0];
+    CK(ctx, cudaSetDevice(d.id));
+    CK(ctx, d.in.ensure(in_len + 16));
+    CK(ctx, cudaMemcpyAsync(d.in.p, in, in_len, cudaMemcpyHostToDevice, d.stream));
+    std::vector<RleBlock> blocks;
+    std::vector<uint32_t> crcs;
+    uint64_t total = 0;
+    int rc = run_rle_device(ctx, d, d.in.as<uint8_t>(), in, in_len, level, blocks, crcs, &total);
+    if (rc != BNZ_OK) return rc;
+    if (blocks.size() > max_blocks) return fail(ctx, BNZ_EINVAL, "max_blocks too small");
+    std::vector<uint8_t> tmp(total);
+    CK(ctx, cudaMemcpyAsync(tmp.data(), d.rle.p, total, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    uint64_t off = 0;
+    for (size_t b = 0; b < blocks.size(); b++) {
+        if (off + blocks[b].n > rle_cap) return fail(ctx, BNZ_EINVAL, "rle_cap too small");
+        blk_in_off[b] = blocks[b].s;
+        blk_in_len[b] = blocks[b].c - blocks[b].s;
+        blk_rle_off[b] = off;
+        blk_rle_len[b] = blocks[b].n;
+        blk_crc[b] = crcs[b];
+        memcpy(rle_out + off, tmp.data() + blocks[b].rle_off, blocks[b].n);
+        off += blocks[b].n;
+    }
+    *n_blocks = blocks.size();
+    return BNZ_OK;
 }
-extern "C" int bnz_encode_file(bnz_ctx *ctx, const char *, const char *, size_t *)
+
+// ---------------------------------------------------------------------------------------
+// MTF / Huffman stages on one device (device-resident batch)
+// ---------------------------------------------------------------------------------------
+
+struct Batch {                      // host description of the blocks resident on a device
+    std::vector<uint64_t> blk_off;  // byte offset of each block image (16-byte aligned)
+    std::vector<uint32_t> blk_len;  // n
+    std::vector<uint64_t> sym_off;  // element offset of each block's symbols
+    std::vector<uint32_t> seg_base; // [nb + 1]
+    std::vector<uint32_t> span_base;// [nb + 1]
+    uint64_t bytes_total = 0;       // size of the rle / bwt / idx arrays
+    uint64_t syms_total = 0;        // elements in the syms array
+    uint32_t max_len = 0;
+    void build()
+    {
+        const size_t nb = blk_len.size();
+        sym_off.resize(nb);
+        seg_base.resize(nb + 1);
+        span_base.resize(nb + 1);
+        uint64_t so = 0;
+        uint32_t sg = 0, sp = 0;
+        const uint32_t gps = huff_groups_per_span();
+        max_len = 0;
+        for (size_t b = 0; b < nb; b++) {
+            sym_off[b] = so;
+            so += ((uint64_t)blk_len[b] + 1 + 15) & ~15ull;
+            seg_base[b] = sg;
+            sg += (blk_len[b] + MTF_SEG - 1) / MTF_SEG;
+            span_base[b] = sp;
+            uint32_t groups = (blk_len[b] + 1 + 49) / 50;            // upper bound: m <= n + 1
+            sp += (groups + gps - 1) / gps;
+            max_len = std::max(max_len, blk_len[b]);
+        }
+        seg_base[nb] = sg;
+        span_base[nb] = sp;
+        syms_total = so;
+    }
+};
+
+template <class X>
+static cudaError_t upload(DevBuf &buf, const std::vector<X> &v, cudaStream_t st)
 {
-    return fail(ctx, BNZ_EINTERNAL, "bnz_encode_file: not implemented yet");
+    cudaError_t e = buf.ensure(v.size() * sizeof(X) + 16);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(X), cudaMemcpyHostToDevice, st);
 }
-extern "C" int bnz_stage_rle1(bnz_ctx *ctx, const uint8_t *, size_t, int, uint64_t *, uint64_t *, uint64_t *,
-                              uint32_t *, uint32_t *, size_t, uint8_t *, size_t, size_t *)
+
+static int upload_batch(bnz_ctx *ctx, Device &d, const Batch &bt)
 {
-    return fail(ctx, BNZ_EINTERNAL, "bnz_stage_rle1: not implemented yet");
+    CK(ctx, upload(d.blk_off, bt.blk_off, d.stream));
+    CK(ctx, upload(d.blk_len, bt.blk_len, d.stream));
+    CK(ctx, upload(d.sym_off, bt.sym_off, d.stream));
+    CK(ctx, upload(d.seg_base, bt.seg_base, d.stream));
+    CK(ctx, upload(d.span_base, bt.span_base, d.stream));
+    return BNZ_OK;
 }
-extern "C" int bnz_stage_mtf(bnz_ctx *ctx, const uint8_t *, const uint64_t *, const uint32_t *, const uint8_t *,
-                             size_t, uint16_t *, uint32_t *, uint32_t *, uint32_t *)
+
+// bwt bytes in d_bwt -> symbols in d.syms (+ sym_len, num_names, freqs); d_idx is scratch of
+// the same size/layout as d_bwt.
+static int run_mtf_device(bnz_ctx *ctx, Device &d, const Batch &bt, const uint8_t *d_bwt, uint8_t *d_idx,
+                          const uint8_t *d_has_byte)
 {
-    return fail(ctx, BNZ_EINTERNAL, "bnz_stage_mtf: not implemented yet");
+    const uint32_t nb = (uint32_t)bt.blk_len.size();
+    const uint32_t segs = bt.seg_base[nb];
+    CK(ctx, d.seg_list.ensure((size_t)segs * 256));
+    CK(ctx, d.seg_cnt.ensure((size_t)segs * 4));
+    CK(ctx, d.seg_state.ensure((size_t)segs * 256));
+    CK(ctx, d.num_names.ensure((size_t)nb * 4));
+    CK(ctx, d.syms.ensure(bt.syms_total * 2));
+    CK(ctx, d.sym_len.ensure((size_t)nb * 4));
+    CK(ctx, d.freqs.ensure((size_t)nb * 258 * 4));
+    MtfArgs a;
+    a.bwt = d_bwt;
+    a.idx = d_idx;
+    a.blk_off = d.blk_off.as<uint64_t>();
+    a.blk_len = d.blk_len.as<uint32_t>();
+    a.has_byte = d_has_byte;
+    a.n_blocks = nb;
+    a.seg_base = d.seg_base.as<uint32_t>();
+    a.total_segs = segs;
+    a.seg_list = d.seg_list.as<uint8_t>();
+    a.seg_cnt = d.seg_cnt.as<uint32_t>();
+    a.seg_state = d.seg_state.as<uint8_t>();
+    a.num_names = d.num_names.as<uint32_t>();
+    a.syms = d.syms.as<uint16_t>();
+    a.sym_off = d.sym_off.as<uint64_t>();
+    a.sym_len = d.sym_len.as<uint32_t>();
+    a.freqs = d.freqs.as<uint32_t>();
+    CK(ctx, mtf_launch(a, d.stream, &d.launches));
+    return BNZ_OK;
 }
-extern "C" int bnz_stage_huffman(bnz_ctx *ctx, const uint16_t *, const uint64_t *, const uint32_t *,
-                                 const uint32_t *, const uint32_t *, size_t, uint8_t *, size_t, uint64_t *,
-                                 uint8_t *, uint32_t *)
+
+static size_t hdr_stride_words(int level)
 {
-    return fail(ctx, BNZ_EINTERNAL, "bnz_stage_huffman: not implemented yet");
+    const size_t smax = ((size_t)100000 * level + 1 + 49) / 50;
+    const size_t bits = 512 + smax + 6 * (5 + 258 * 33);
+    return ((bits + 31) / 32 + 3) & ~(size_t)3;
+}
+
+static void fill_huff_args(HuffArgs &a, Device &d, const Batch &bt, int level)
+{
+    const uint32_t nb = (uint32_t)bt.blk_len.size();
+    memset(&a, 0, sizeof a);
+    a.syms = d.syms.as<uint16_t>();
+    a.sym_off = d.sym_off.as<uint64_t>();
+    a.sym_len = d.sym_len.as<uint32_t>();
+    a.num_names = d.num_names.as<uint32_t>();
+    a.freqs = d.freqs.as<uint32_t>();
+    a.n_blocks = nb;
+    a.lens = d.lens.as<uint8_t>();
+    a.codes = d.codes.as<uint32_t>();
+    a.tf = d.tf.as<uint32_t>();
+    a.num_tables = d.num_tables.as<uint32_t>();
+    a.num_sel = d.num_sel.as<uint32_t>();
+    a.selectors = nullptr;
+    a.sel_stride = 0;
+    a.span_base = d.span_base.as<uint32_t>();
+    a.hdr = d.hdr.as<uint32_t>();
+    a.hdr_stride = hdr_stride_words(level);
+    a.hdr_bits = d.hdr_bits.as<uint32_t>();
+    a.crc = d.crc.as<uint32_t>();
+    a.ptr = d.ptr.as<uint32_t>();
+    a.has_byte = d.has_byte.as<uint8_t>();
+    a.blk_bits = d.blk_bits.as<uint64_t>();
+    a.blk_bitoff = d.blk_bitoff.as<uint64_t>();
+    a.total_bits = d.total_bits.as<uint64_t>();
+    a.out_words = d.out.as<uint32_t>();
+}
+
+// modelling + tables + headers + bit offsets; leaves total bits (bit_base + sum) in *total_bits_host
+static int run_huff_model_device(bnz_ctx *ctx, Device &d, const Batch &bt, int level, int with_block_header,
+                                 uint64_t bit_base, uint64_t fixed_stride_bits, HuffArgs &a)
+{
+    const uint32_t nb = (uint32_t)bt.blk_len.size();
+    const size_t tsz = (size_t)nb * HUFF_MAX_TABLES * HUFF_MAX_SYMS;
+    CK(ctx, d.lens.ensure(tsz));
+    CK(ctx, d.codes.ensure(tsz * 4));
+    CK(ctx, d.tf.ensure(tsz * 4));
+    CK(ctx, d.num_tables.ensure((size_t)nb * 4));
+    CK(ctx, d.num_sel.ensure((size_t)nb * 4));
+    CK(ctx, d.hdr.ensure((size_t)nb * hdr_stride_words(level) * 4));
+    CK(ctx, d.hdr_bits.ensure((size_t)nb * 4));
+    CK(ctx, d.blk_bits.ensure((size_t)nb * 8));
+    CK(ctx, d.blk_bitoff.ensure((size_t)nb * 8));
+    CK(ctx, d.total_bits.ensure(64));
+    CK(ctx, cudaMemsetAsync(d.tf.p, 0, tsz * 4, d.stream));
+    fill_huff_args(a, d, bt, level);
+    a.with_block_header = with_block_header;
+    a.bit_base = bit_base;
+    a.fixed_stride_bits = fixed_stride_bits;
+    CK(ctx, huff_launch(a, bt.span_base[nb], d.stream, &d.launches));
+    return BNZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// stage exports: MTF and Huffman
+// ---------------------------------------------------------------------------------------
+
+extern "C" int bnz_stage_mtf(bnz_ctx *ctx, const uint8_t *bwt, const uint64_t *blk_off, const uint32_t *blk_len,
+                             const uint8_t *has_byte, size_t n_blocks, uint16_t *syms_out, uint32_t *sym_len,
+                             uint32_t *num_syms, uint32_t *freqs_out)
+{
+    if (!ctx) return BNZ_EINVAL;
+    if (n_blocks == 0) return BNZ_OK;
+    if (!bwt || !blk_off || !blk_len || !has_byte || !syms_out || !sym_len || !num_syms || !freqs_out)
+        return BNZ_EINVAL;
+    Device &d = ctx->devs[0];
+    CK(ctx, cudaSetDevice(d.id));
+    Batch bt;
+    bt.blk_off.resize(n_blocks);
+    bt.blk_len.assign(blk_len, blk_len + n_blocks);
+    uint64_t off = 0;
+    for (size_t b = 0; b < n_blocks; b++) {
+        if (blk_len[b] == 0 || blk_len[b] > 900000) return BNZ_EINVAL;
+        bt.blk_off[b] = off;
+        off += ((uint64_t)blk_len[b] + 15) & ~15ull;
+    }
+    bt.bytes_total = off;
+    bt.build();
+    CK(ctx, d.bwt.ensure(off));
+    CK(ctx, d.rle.ensure(off));
+    CK(ctx, d.has_byte.ensure(n_blocks * 256));
+    for (size_t b = 0; b < n_blocks; b++)
+        CK(ctx, cudaMemcpyAsync(d.bwt.as<uint8_t>() + bt.blk_off[b], bwt + blk_off[b], blk_len[b],
+                                cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemcpyAsync(d.has_byte.p, has_byte, n_blocks * 256, cudaMemcpyHostToDevice, d.stream));
+    int rc = upload_batch(ctx, d, bt);
+    if (rc != BNZ_OK) return rc;
+    rc = run_mtf_device(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>());
+    if (rc != BNZ_OK) return rc;
+    std::vector<uint32_t> nn(n_blocks);
+    CK(ctx, cudaMemcpyAsync(sym_len, d.sym_len.p, n_blocks * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaMemcpyAsync(nn.data(), d.num_names.p, n_blocks * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaMemcpyAsync(freqs_out, d.freqs.p, n_blocks * 258 * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    for (size_t b = 0; b < n_blocks; b++) {
+        num_syms[b] = nn[b] + 2;
+        CK(ctx, cudaMemcpyAsync(syms_out + blk_off[b] + b, d.syms.as<uint16_t>() + bt.sym_off[b],
+                                (size_t)sym_len[b] * 2, cudaMemcpyDeviceToHost, d.stream));
+    }
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    return BNZ_OK;
+}
+
+extern "C" int bnz_stage_huffman(bnz_ctx *ctx, const uint16_t *syms, const uint64_t *sym_off,
+                                 const uint32_t *sym_len, const uint32_t *num_syms, const uint32_t *freqs,
+                                 size_t n_blocks, uint8_t *bits_out, size_t out_stride, uint64_t *bit_len,
+                                 uint8_t *tables_out, uint32_t *num_tables)
+{
+    if (!ctx) return BNZ_EINVAL;
+    if (n_blocks == 0) return BNZ_OK;
+    if (!syms || !sym_off || !sym_len || !num_syms || !freqs || !bits_out || !bit_len || !tables_out ||
+        !num_tables || (out_stride & 3))
+        return BNZ_EINVAL;
+    Device &d = ctx->devs[0];
+    CK(ctx, cudaSetDevice(d.id));
+    Batch bt;
+    bt.blk_off.resize(n_blocks);
+    bt.blk_len.resize(n_blocks);
+    std::vector<uint32_t> nn(n_blocks);
+    uint64_t off = 0;
+    for (size_t b = 0; b < n_blocks; b++) {
+        if (sym_len[b] < 1 || sym_len[b] > 900001 || num_syms[b] < 3 || num_syms[b] > 258) return BNZ_EINVAL;
+        bt.blk_len[b] = sym_len[b] - 1;        // m <= n + 1 bookkeeping
+        if (bt.blk_len[b] == 0) bt.blk_len[b] = 1;
+        bt.blk_off[b] = off;
+        off += ((uint64_t)bt.blk_len[b] + 15) & ~15ull;
+        nn[b] = num_syms[b] - 2;
+    }
+    bt.build();
+    int rc = upload_batch(ctx, d, bt);
+    if (rc != BNZ_OK) return rc;
+    CK(ctx, d.syms.ensure(bt.syms_total * 2));
+    CK(ctx, d.sym_len.ensure(n_blocks * 4));
+    CK(ctx, d.num_names.ensure(n_blocks * 4));
+    CK(ctx, d.freqs.ensure(n_blocks * 258 * 4));
+    for (size_t b = 0; b < n_blocks; b++)
+        CK(ctx, cudaMemcpyAsync(d.syms.as<uint16_t>() + bt.sym_off[b], syms + sym_off[b], (size_t)sym_len[b] * 2,
+                                cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemcpyAsync(d.sym_len.p, sym_len, n_blocks * 4, cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemcpyAsync(d.num_names.p, nn.data(), n_blocks * 4, cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemcpyAsync(d.freqs.p, freqs, n_blocks * 258 * 4, cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, d.out.ensure(n_blocks * out_stride + 64));
+    CK(ctx, cudaMemsetAsync(d.out.p, 0, n_blocks * out_stride + 64, d.stream));
+    HuffArgs a;
+    rc = run_huff_model_device(ctx, d, bt, 9, 0, 0, (uint64_t)out_stride * 8, a);
+    if (rc != BNZ_OK) return rc;
+    a.out_words = d.out.as<uint32_t>();
+    CK(ctx, huff_pack_launch(a, d.stream, &d.launches));
+    std::vector<uint64_t> bb(n_blocks);
+    CK(ctx, cudaMemcpyAsync(bb.data(), d.blk_bits.p, n_blocks * 8, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaMemcpyAsync(num_tables, d.num_tables.p, n_blocks * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaMemcpyAsync(tables_out, d.lens.p, n_blocks * HUFF_MAX_TABLES * HUFF_MAX_SYMS,
+                            cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaMemcpyAsync(bits_out, d.out.p, n_blocks * out_stride, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    for (size_t b = 0; b < n_blocks; b++) {
+        bit_len[b] = bb[b];
+        if ((bb[b] + 7) / 8 > out_stride) return fail(ctx, BNZ_EINVAL, "out_stride too small");
+    }
+    return BNZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// bnz_encode: the whole path
+// ---------------------------------------------------------------------------------------
+
+static void put_bits_host(uint8_t *buf, uint64_t bitpos, uint64_t value, int nbits)   // MSB first
+{
+    for (int i = nbits - 1; i >= 0; i--, bitpos++)
+        if ((value >> i) & 1) buf[bitpos >> 3] |= (uint8_t)(0x80u >> (bitpos & 7));
+}
+
+// Encodes on device 0.  d_in: device copy of the input (uploaded here when null), h_in: host
+// copy.  The finished stream is left in d.out (bytes [0, *out_len)) — header and footer are
+// patched on the host side by the callers.
+static int encode_single(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in_given, size_t N, int level,
+                         std::vector<uint32_t> &crcs, uint64_t *total_bits_out)
+{
+    Device &d = ctx->devs[0];
+    bnz_stats &st = ctx->stats;
+    CK(ctx, cudaSetDevice(d.id));
+    d.launches = 0;
+    const uint8_t *d_in = d_in_given;
+    CK(ctx, cudaEventRecord(d.ev[0], d.stream));
+    if (!d_in) {
+        CK(ctx, d.in.ensure(N + 64));
+        CK(ctx, cudaMemcpyAsync(d.in.p, h_in, N, cudaMemcpyHostToDevice, d.stream));
+        d_in = d.in.as<uint8_t>();
+        st.h2d_bytes += N;
+    }
+    CK(ctx, cudaEventRecord(d.ev[1], d.stream));
+
+    // K1/K2
+    std::vector<RleBlock> blocks;
+    uint64_t rle_total = 0;
+    int rc = run_rle_device(ctx, d, d_in, h_in, N, level, blocks, crcs, &rle_total);
+    if (rc != BNZ_OK) return rc;
+    CK(ctx, cudaEventRecord(d.ev[2], d.stream));
+    const uint32_t nb = (uint32_t)blocks.size();
+    Batch bt;
+    bt.blk_off.resize(nb);
+    bt.blk_len.resize(nb);
+    for (uint32_t b = 0; b < nb; b++) {
+        bt.blk_off[b] = blocks[b].rle_off;
+        bt.blk_len[b] = blocks[b].n;
+    }
+    bt.bytes_total = rle_total;
+    bt.build();
+    rc = upload_batch(ctx, d, bt);
+    if (rc != BNZ_OK) return rc;
+    CK(ctx, upload(d.crc, crcs, d.stream));
+
+    // K3/K4
+    CK(ctx, d.bwt.ensure(rle_total));
+    CK(ctx, d.ptr.ensure((size_t)nb * 4));
+    CK(ctx, d.has_byte.ensure((size_t)nb * 256));
+    CK(ctx, d.bwt_stats.ensure((size_t)nb * sizeof(BwtStats)));
+    rc = run_bwt_device(ctx, d, d.rle.as<uint8_t>(), d.bwt.as<uint8_t>(), d.blk_off.as<uint64_t>(),
+                        d.blk_len.as<uint32_t>(), nb, bt.max_len, d.ptr.as<uint32_t>(), d.has_byte.as<uint8_t>(),
+                        d.bwt_stats.as<BwtStats>());
+    if (rc != BNZ_OK) return rc;
+    CK(ctx, cudaEventRecord(d.ev[3], d.stream));
+
+    // K5 (the RLE1 images are dead now: reuse their buffer for the MTF index bytes)
+    rc = run_mtf_device(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>());
+    if (rc != BNZ_OK) return rc;
+    CK(ctx, cudaEventRecord(d.ev[4], d.stream));
+
+    // K6/K7 + headers + offsets
+    HuffArgs ha;
+    rc = run_huff_model_device(ctx, d, bt, level, 1, 32, 0, ha);
+    if (rc != BNZ_OK) return rc;
+    uint64_t total_bits = 0;
+    std::vector<BwtStats> bst(nb);
+    CK(ctx, cudaMemcpyAsync(&total_bits, d.total_bits.p, 8, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaMemcpyAsync(bst.data(), d.bwt_stats.p, (size_t)nb * sizeof(BwtStats), cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaEventRecord(d.ev[5], d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+
+    // K8
+    const size_t out_bytes = (size_t)((total_bits + 80 + 7) / 8);
+    CK(ctx, d.out.ensure(out_bytes + 64));
+    CK(ctx, cudaMemsetAsync(d.out.p, 0, ((out_bytes + 63) & ~(size_t)63), d.stream));
+    ha.out_words = d.out.as<uint32_t>();
+    CK(ctx, huff_pack_launch(ha, d.stream, &d.launches));
+    CK(ctx, cudaEventRecord(d.ev[6], d.stream));
+    *total_bits_out = total_bits;
+
+    st.n_blocks = nb;
+    for (uint32_t b = 0; b < nb; b++) {
+        st.bwt_n += bst[b].n;
+        st.bwt_sum_active += bst[b].sum_active;
+        st.bwt_sum_active_passes += bst[b].sum_active_passes;
+        st.bwt_rounds_total += bst[b].rounds;
+        st.bwt_max_rounds = std::max(st.bwt_max_rounds, bst[b].rounds);
+        st.bwt_tied_blocks += bst[b].tied;
+    }
+    st.bwt_algorithmic_bytes = 9 * st.bwt_n + 16 * st.bwt_sum_active_passes + 36 * st.bwt_sum_active;
+    return BNZ_OK;
+}
+
+static void finish_stats(bnz_ctx *ctx, Device &d, bool have_d2h)
+{
+    bnz_stats &st = ctx->stats;
+    auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, d.ev[a], d.ev[b]); return ms; };
+    st.h2d_ms = el(0, 1);
+    st.rle_ms = el(1, 2);
+    st.bwt_ms = el(2, 3);
+    st.mtf_ms = el(3, 4);
+    st.huff_ms = el(4, 5);
+    st.pack_ms = el(5, 6);
+    st.d2h_ms = have_d2h ? el(6, 7) : 0.f;
+    st.total_ms = el(0, have_d2h ? 7 : 6);
+    st.kernel_launches = d.launches;
+    st.n_devices = 1;
+    st.bwt_radix_bits = (uint32_t)ctx->radix_bits;
+}
+
+static uint32_t fold_stream_crc(const std::vector<uint32_t> &crcs)       // lib.rs:108
+{
+    uint32_t s = 0;
+    for (uint32_t c : crcs) s = c ^ ((s << 1) | (s >> 31));
+    return s;
+}
+
+extern "C" int bnz_encode(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int level, uint8_t **out,
+                          size_t *out_len, size_t *consumed)
+{
+    if (!ctx || !out || !out_len) return BNZ_EINVAL;
+    *out = nullptr;
+    *out_len = 0;
+    if (consumed) *consumed = 0;
+    if (level < 1 || level > 9) return fail(ctx, BNZ_EINVAL, "level must be in 1..=9 (lib/lib.rs:89)");
+    if (in_len && !in) return BNZ_EINVAL;
+    if (ctx->out_cache_lent) return fail(ctx, BNZ_EINVAL, "previous output not released with bnz_free");
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->stats.in_bytes = in_len;
+    Device &d = ctx->devs[0];
+    CK(ctx, cudaSetDevice(d.id));
+
+    uint64_t total_bits = 32;
+    std::vector<uint32_t> crcs;
+    if (in_len > 0) {
+        int rc = encode_single(ctx, in, nullptr, in_len, level, crcs, &total_bits);
+        if (rc != BNZ_OK) return rc;
+    }
+    const size_t nbytes = (size_t)((total_bits + 80 + 7) / 8);
+    if (ctx->out_cache_cap < nbytes + 16) {
+        if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
+        ctx->out_cache = nullptr;
+        ctx->out_cache_cap = 0;
+        size_t want = nbytes + nbytes / 4 + 4096;
+        CK(ctx, cudaHostAlloc((void **)&ctx->out_cache, want, cudaHostAllocPortable));
+        ctx->out_cache_cap = want;
+    }
+    uint8_t *o = ctx->out_cache;
+    if (in_len > 0) {
+        CK(ctx, cudaMemcpyAsync(o, d.out.p, nbytes, cudaMemcpyDeviceToHost, d.stream));
+        CK(ctx, cudaEventRecord(d.ev[7], d.stream));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+        ctx->stats.d2h_bytes += nbytes;
+        finish_stats(ctx, d, true);
+    } else {
+        memset(o, 0, nbytes);
+    }
+    // stream header (lib.rs:18-22), footer (lib.rs:66-70), zero padding (out.rs:22-28)
+    o[0] = 0x42; o[1] = 0x5A; o[2] = 0x68; o[3] = (uint8_t)('0' + level);
+    put_bits_host(o, total_bits, 0x177245385090ull, 48);
+    put_bits_host(o, total_bits + 48, fold_stream_crc(crcs), 32);
+    ctx->stats.out_bytes = nbytes;
+    ctx->out_cache_lent = true;
+    *out = o;
+    *out_len = nbytes;
+    if (consumed) *consumed = in_len;
+    return BNZ_OK;
+}
+
+extern "C" void bnz_free(bnz_ctx *ctx, uint8_t *p)
+{
+    if (!ctx || !p) return;
+    if (p == ctx->out_cache) ctx->out_cache_lent = false;
+}
+
+extern "C" int bnz_encode_device(bnz_ctx *ctx, const void *d_in, const uint8_t *h_in, size_t in_len, int level,
+                                 void *d_out, size_t d_out_cap, size_t *out_len)
+{
+    if (!ctx || !out_len || !d_out) return BNZ_EINVAL;
+    *out_len = 0;
+    if (level < 1 || level > 9) return fail(ctx, BNZ_EINVAL, "level must be in 1..=9 (lib/lib.rs:89)");
+    if (in_len == 0 || !d_in || !h_in) return BNZ_EINVAL;
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->stats.in_bytes = in_len;
+    Device &d = ctx->devs[0];
+    uint64_t total_bits = 32;
+    std::vector<uint32_t> crcs;
+    int rc = encode_single(ctx, h_in, (const uint8_t *)d_in, in_len, level, crcs, &total_bits);
+    if (rc != BNZ_OK) return rc;
+    const size_t nbytes = (size_t)((total_bits + 80 + 7) / 8);
+    if (nbytes > d_out_cap) return fail(ctx, BNZ_EINVAL, "d_out_cap too small");
+    // header / footer patched into the device stream: 4 + 10(+1) bytes
+    uint8_t tail[16] = { 0 };
+    const uint64_t tb = total_bits & 7;
+    uint8_t lastbyte = 0;
+    if (tb) CK(ctx, cudaMemcpyAsync(&lastbyte, d.out.as<uint8_t>() + (total_bits >> 3), 1, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    tail[0] = lastbyte;
+    put_bits_host(tail, tb, 0x177245385090ull, 48);
+    put_bits_host(tail, tb + 48, fold_stream_crc(crcs), 32);
+    const uint8_t head[4] = { 0x42, 0x5A, 0x68, (uint8_t)('0' + level) };
+    CK(ctx, cudaMemcpyAsync(d.out.p, head, 4, cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemcpyAsync(d.out.as<uint8_t>() + (total_bits >> 3), tail, nbytes - (total_bits >> 3),
+                            cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemcpyAsync(d_out, d.out.p, nbytes, cudaMemcpyDeviceToDevice, d.stream));
+    CK(ctx, cudaEventRecord(d.ev[7], d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    finish_stats(ctx, d, false);
+    ctx->stats.out_bytes = nbytes;
+    *out_len = nbytes;
+    return BNZ_OK;
+}
+
+extern "C" int bnz_encode_file(bnz_ctx *ctx, const char *in_path, const char *out_path, size_t *consumed)
+{
+    if (!ctx || !in_path || !out_path) return BNZ_EINVAL;
+    FILE *f = fopen(in_path, "rb");
+    if (!f) return fail(ctx, BNZ_EINVAL, std::string("cannot open ") + in_path);
+    std::vector<uint8_t> data;
+    uint8_t tmp[1 << 16];
+    size_t got;
+    while ((got = fread(tmp, 1, sizeof tmp, f)) > 0) data.insert(data.end(), tmp, tmp + got);
+    fclose(f);
+    uint8_t *out = nullptr;
+    size_t out_len = 0, cons = 0;
+    int rc = bnz_encode(ctx, data.data(), data.size(), 9, &out, &out_len, &cons);     // lib.rs:152: level 9
+    if (rc != BNZ_OK) return rc;
+    FILE *g = fopen(out_path, "wb");
+    if (!g) {
+        bnz_free(ctx, out);
+        return fail(ctx, BNZ_EINVAL, std::string("cannot create ") + out_path);
+    }
+    size_t wrote = fwrite(out, 1, out_len, g);
+    fclose(g);
+    bnz_free(ctx, out);
+    if (wrote != out_len) return fail(ctx, BNZ_EINVAL, "short write");
+    if (consumed) *consumed = cons;
+    return BNZ_OK;
 }

@@ -66,9 +66,11 @@ BNZ_API void bnz_free(bnz_ctx *ctx, uint8_t *p);
 
 /* Same computation with the input already resident in device memory of the context's
  * first device and the stream left on the device (used to time the kernels without
- * PCIe).  d_out must hold bnz_max_compressed_size(in_len) bytes. */
-BNZ_API int bnz_encode_device(bnz_ctx *ctx, const void *d_in, size_t in_len, int level,
-                              void *d_out, size_t d_out_cap, size_t *out_len);
+ * PCIe).  h_in is the host mirror of the same bytes: the sequential block-cut walk
+ * (lib/rle.rs capacity rule) reads <= 2 KiB of it per block; nothing is uploaded.
+ * d_out must hold bnz_max_compressed_size(in_len) bytes (or the exact size if known). */
+BNZ_API int bnz_encode_device(bnz_ctx *ctx, const void *d_in, const uint8_t *h_in, size_t in_len,
+                              int level, void *d_out, size_t d_out_cap, size_t *out_len);
 BNZ_API size_t bnz_max_compressed_size(size_t in_len);
 
 /* `banzai::encode_file(in_path, out_path)` (lib/lib.rs:141-153): level 9, returns bytes
