@@ -32,6 +32,7 @@ class Stats(C.Structure):
         ("bwt_sum_active_passes", C.c_uint64),
         ("bwt_max_rounds", C.c_uint32), ("bwt_tied_blocks", C.c_uint32),
         ("bwt_rounds_total", C.c_uint64), ("bwt_algorithmic_bytes", C.c_uint64),
+        ("bwt_cyc_build", C.c_uint64), ("bwt_cyc_radix", C.c_uint64), ("bwt_cyc_rerank", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
     ]
 

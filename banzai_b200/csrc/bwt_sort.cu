@@ -53,13 +53,16 @@ struct Cfg {
 };
 
 template <int BITS>
-struct __align__(16) Smem {
+struct __align__(128) Smem {
+    u64 inbuf[TILE];                                      // TMA landing zone for the next tile
     u64 stage[TILE];                                      // tile reorder buffer
     u16 whist[NW][Cfg<BITS>::BINS];                       // per-warp digit counts / offsets
     u32 cursor[Cfg<BITS>::BINS];                          // running bucket cursors (global)
     u32 binoff[Cfg<BITS>::BINS];                          // exclusive bin offsets inside the tile
     u32 gbase[Cfg<BITS>::BINS];                           // cursor - binoff
     u32 hist[Cfg<BITS>::PASSES][Cfg<BITS>::BINS];         // per-pass digit histograms
+    u64 scratch64[40];
+    u64 mbar;                                             // mbarrier of the TMA tile pipeline
     u32 scratch[40];
     u32 s_count;                                          // records appended by build_*
     u32 s_block;                                          // claimed block id
@@ -132,18 +135,28 @@ __device__ void build_round(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h,
     hist_clear(sm);
     const u32 hm = h % n;
     for (u32 base = 0; base < n; base += TILE) {
+        // all loads first (rank[i], then the rank[i+h] gathers) so their latencies overlap
+        u32 r[K], r2[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
             u32 i = base + k * T + threadIdx.x;
-            u32 r = (i < n) ? rank[i] : DONE;
-            bool act = !(r & DONE);
-            u64 rec = 0;
-            if (act) {
+            r[k] = (i < n) ? rank[i] : DONE;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            u32 i = base + k * T + threadIdx.x;
+            r2[k] = 0;
+            if (!(r[k] & DONE)) {
                 u32 j = i + hm;
                 if (j >= n) j -= n;
-                u32 r2 = rank[j] & RANK_MASK;
-                rec = ((u64)r << (IDX_BITS + 20)) | ((u64)r2 << IDX_BITS) | i;
+                r2[k] = rank[j];
             }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            u32 i = base + k * T + threadIdx.x;
+            bool act = !(r[k] & DONE);
+            u64 rec = ((u64)r[k] << (IDX_BITS + 20)) | ((u64)(r2[k] & RANK_MASK) << IDX_BITS) | i;
             u32 m = __ballot_sync(0xffffffffu, act);
             if (m) {
                 u32 wbase = 0;
@@ -159,26 +172,51 @@ __device__ void build_round(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h,
     __syncthreads();
 }
 
-// One LSD pass over `count` records: src -> dst by digit `pass`.
+// warp-wide "which lanes hold my digit": BITS ballots (cheaper than match.any here)
 template <int BITS>
-__device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst,
-                           u32 count, int pass)
+__device__ __forceinline__ u32 match_digit(u32 d)
+{
+    u32 peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const u32 bit = (d >> b) & 1u;
+        const u32 vote = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? vote : ~vote;
+    }
+    return peers;
+}
+
+// One LSD pass over `count` records: src -> dst by digit `pass`.
+// Tiles are streamed through shared memory with TMA bulk copies (cp.async.bulk + mbarrier):
+// the copy of tile t+1 is in flight while tile t is ranked, reordered and stored.
+template <int BITS>
+__device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, int pass, u32 &phase)
 {
     constexpr int BINS = Cfg<BITS>::BINS;
     constexpr int BPT = Cfg<BITS>::BPT;
+    constexpr int NSCAN = BINS / BPT;               // threads that own bins in the scans
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
+
+    // records were written with generic-proxy stores; order them before the async-proxy reads
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+        const u32 bytes = (min((u32)TILE, count) * 8u + 15u) & ~15u;
+        mbar_expect_tx(&sm.mbar, bytes);
+        tma_load_1d(sm.inbuf, src, bytes, &sm.mbar);
+    }
 
     // cursor = exclusive scan of this pass's histogram
     {
-        u32 c[BPT], s = 0;
+        u32 c[BPT], sum = 0;
 #pragma unroll
         for (int j = 0; j < BPT; j++) {
             u32 b = tid * BPT + j;
             c[j] = (b < BINS) ? sm.hist[pass][b] : 0;
-            s += c[j];
+            sum += c[j];
         }
         u32 tot;
-        u32 ex = block_excl_sum<T>(s, sm.scratch, &tot);
+        u32 ex = block_excl_sum<T>(sum, sm.scratch, &tot);
 #pragma unroll
         for (int j = 0; j < BPT; j++) {
             u32 b = tid * BPT + j;
@@ -192,19 +230,21 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst,
         const u32 tile_n = min((u32)TILE, count - base);
         u64 rec[K];
         u32 rk[K];
-        const u32 wbase = base + w * (K * 32) + lane;
+        for (int b = lane; b < BINS; b += 32) sm.whist[w][b] = 0;
+        mbar_wait(&sm.mbar, phase);
+        phase ^= 1u;
+        const u32 wl = w * (K * 32) + lane;
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            u32 j = wbase + k * 32;
-            rec[k] = (j < count) ? src[j] : ~0ull;
+            u32 j = wl + k * 32;
+            rec[k] = (j < tile_n) ? sm.inbuf[j] : ~0ull;
         }
-        for (int b = lane; b < BINS; b += 32) sm.whist[w][b] = 0;
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            u32 d = digit_of<BITS>(rec[k], pass);
-            u32 peers = __match_any_sync(0xffffffffu, d);
-            u32 leader = 31 - __clz(peers);
+            const u32 d = digit_of<BITS>(rec[k], pass);
+            const u32 peers = match_digit<BITS>(d);
+            const u32 leader = 31 - __clz(peers);
             u32 bcount = 0;
             if (lane == leader) {
                 bcount = sm.whist[w][d];
@@ -214,61 +254,69 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst,
             rk[k] = bcount + __popc(peers & lanemask_lt());
             __syncwarp();
         }
-        __syncthreads();
+        __syncthreads();                                        // B1: inbuf consumed, whist complete
 
-        // cross-warp exclusive scan per bin, then exclusive scan over bins
-        {
-            u32 c[BPT], s = 0;
+        if (tid == 0 && base + TILE < count) {                  // prefetch the next tile
+            const u32 nb = (min((u32)TILE, count - base - TILE) * 8u + 15u) & ~15u;
+            fence_proxy_async();
+            mbar_expect_tx(&sm.mbar, nb);
+            tma_load_1d(sm.inbuf, src + base + TILE, nb, &sm.mbar);
+        }
+
+        // cross-warp exclusive scan per bin, then exclusive scan over bins (NSCAN threads)
+        if (tid < NSCAN) {
+            u32 c[BPT], sum = 0;
 #pragma unroll
             for (int j = 0; j < BPT; j++) {
-                u32 b = tid * BPT + j;
+                const u32 b = tid * BPT + j;
                 u32 run = 0;
-                if (b < BINS) {
 #pragma unroll
-                    for (int ww = 0; ww < NW; ww++) {
-                        u32 v = sm.whist[ww][b];
-                        sm.whist[ww][b] = (u16)run;
-                        run += v;
-                    }
+                for (int ww = 0; ww < NW; ww++) {
+                    u32 v = sm.whist[ww][b];
+                    sm.whist[ww][b] = (u16)run;
+                    run += v;
                 }
                 c[j] = run;
-                s += run;
+                sum += run;
             }
-            u32 tot;
-            u32 ex = block_excl_sum<T>(s, sm.scratch, &tot);
+            const u32 inc = warp_incl_sum(sum);
+            if (lane == 31) sm.scratch[w] = inc;
+            asm volatile("bar.sync 1, %0;" ::"n"(NSCAN) : "memory");
+            u32 woff = 0;
+            for (u32 q = 0; q < w; q++) woff += sm.scratch[q];
+            u32 ex = woff + inc - sum;
 #pragma unroll
             for (int j = 0; j < BPT; j++) {
-                u32 b = tid * BPT + j;
-                if (b < BINS) {
-                    u32 cur = sm.cursor[b];
-                    sm.binoff[b] = ex;
-                    sm.gbase[b] = cur - ex;
-                    sm.cursor[b] = cur + c[j];
-                }
+                const u32 b = tid * BPT + j;
+                const u32 cur = sm.cursor[b];
+                sm.binoff[b] = ex;
+                sm.gbase[b] = cur - ex;
+                sm.cursor[b] = cur + c[j];
                 ex += c[j];
             }
         }
-        __syncthreads();
+        __syncthreads();                                        // B2
 
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            u32 d = digit_of<BITS>(rec[k], pass);
-            u32 pos = sm.binoff[d] + sm.whist[w][d] + rk[k];
+            const u32 d = digit_of<BITS>(rec[k], pass);
+            const u32 pos = sm.binoff[d] + sm.whist[w][d] + rk[k];
             sm.stage[pos] = rec[k];
         }
-        __syncthreads();
+        __syncthreads();                                        // B3
 
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            u32 j = k * T + tid;
+            const u32 j = k * T + tid;
             if (j < tile_n) {
-                u64 r = sm.stage[j];
-                u32 d = digit_of<BITS>(r, pass);
+                const u64 r = sm.stage[j];
+                const u32 d = digit_of<BITS>(r, pass);
                 dst[sm.gbase[d] + j] = r;
             }
         }
-        __syncthreads();
+        // no barrier here: the next tile's B1 orders these reads before stage/whist are reused
     }
+    __syncthreads();
 }
 
 struct RerankOut {
@@ -315,38 +363,53 @@ __device__ RerankOut rerank(Smem<BITS> &sm, const u64 *src, u32 count, bool init
             pk[k] = mk;
             pg[k] = mg;
         }
-        u32 tot_k, tot_g;
-        u32 ex_k = block_excl_max<T>(mk, sm.scratch, &tot_k);
-        u32 ex_g = block_excl_max<T>(mg, sm.scratch, &tot_g);
-        ex_k = max(ex_k, carry_key);
-        ex_g = max(ex_g, carry_grp);
+        u64 tot2;
+        const u64 ex2 = block_excl_max2<T>(((u64)mg << 32) | mk, sm.scratch64, &tot2);
+        const u32 ex_k = max((u32)ex2, carry_key);
+        const u32 ex_g = max((u32)(ex2 >> 32), carry_grp);
+        const u32 tot_k = (u32)tot2, tot_g = (u32)(tot2 >> 32);
 
+        u32 nrv[K];
+        u32 flg[K];                          // bit0 valid, bit1 singleton
+        u32 sb[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
             u32 j = j0 + k;
+            flg[k] = 0;
+            nrv[k] = 0;
             if (j < count) {
                 u32 p_key = max(pk[k], ex_k);        // 1-based
                 u32 p_grp = max(pg[k], ex_g);
                 bool hk = (pk[k] == j + 1);
                 bool hg = (pg[k] == j + 1);
                 u32 r1 = initial ? 0u : (u32)(key[k + 1] >> 20) & RANK_MASK;
-                u32 nr = r1 + (p_key - p_grp);
+                nrv[k] = r1 + (p_key - p_grp);
                 bool single = hk && (j + 1 == count || key[k + 2] != key[k + 1]);
-                u32 id = idx[k];
-                if (single) {
-                    rank[id] = nr | DONE;
-                    bwt_out[nr] = S[id == 0 ? n - 1 : id - 1];
-                    if (id == 0) *ptr_out = nr;
-                } else {
-                    rank[id] = nr;
-                    n_active++;
-                }
+                flg[k] = 1u | (single ? 2u : 0u);
+                if (!single) n_active++;
                 if (hk && !hg) n_split++;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            sb[k] = 0;
+            if (flg[k] & 2u) sb[k] = S[idx[k] == 0 ? n - 1 : idx[k] - 1];
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (flg[k] & 1u) {
+                const u32 id = idx[k];
+                if (flg[k] & 2u) {
+                    rank[id] = nrv[k] | DONE;
+                    bwt_out[nrv[k]] = (u8)sb[k];
+                    if (id == 0) *ptr_out = nrv[k];
+                } else {
+                    rank[id] = nrv[k];
+                }
             }
         }
         carry_key = max(carry_key, tot_k);
         carry_grp = max(carry_grp, tot_g);
-        __syncthreads();
     }
     RerankOut o;
     o.active = block_sum<T>(n_active, sm.scratch);
@@ -405,10 +468,17 @@ __device__ void finalize_ties(Smem<BITS> &sm, const u64 *src, u32 count,
 template <int BITS>
 __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<BITS> &sm = *reinterpret_cast<Smem<BITS> *>(smem_raw);
     constexpr int PASSES = Cfg<BITS>::PASSES;
     const u32 tid = threadIdx.x;
+
+    if (tid == 0) {
+        mbar_init(&sm.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    u32 phase = 0;                       // parity of the next TMA completion
 
     u64 *bufA = a.ws_rec + (size_t)blockIdx.x * 2 * a.ws_stride;
     u64 *bufB = bufA + a.ws_stride;
@@ -428,15 +498,19 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
 
         u32 rounds = 0;
         u64 sum_active = 0, sum_active_passes = 0;
+        long long cyc_build = 0, cyc_radix = 0, cyc_rerank = 0, t0, t1;
         u32 h = 5;
         u32 count = n;
         bool initial = true;
         bool tied = false;
 
         while (count > 0 && rounds < MAX_ROUNDS) {
+            t0 = clock64();
             if (initial) build_initial<BITS>(sm, S, n, bufA);
             else build_round<BITS>(sm, rank, n, h, bufA);
             count = sm.s_count;
+            t1 = clock64();
+            cyc_build += t1 - t0;
 
             u64 *src = bufA, *dst = bufB;
             u32 passes_run = 0;
@@ -450,7 +524,7 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
                 const bool skip = sm.s_flags[0] != 0;
                 __syncthreads();
                 if (skip) continue;
-                radix_pass<BITS>(sm, src, dst, count, p);
+                radix_pass<BITS>(sm, src, dst, count, p, phase);
                 u64 *t = src; src = dst; dst = t;
                 passes_run++;
             }
@@ -458,8 +532,11 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
             sum_active_passes += (u64)count * passes_run;
             rounds++;
 
+            t0 = clock64();
+            cyc_radix += t0 - t1;
             RerankOut ro = rerank<BITS>(sm, src, count, initial, S, n, rank, bwt_out, ptr_out);
             __syncthreads();
+            cyc_rerank += clock64() - t0;
             if (ro.active > 0 && ro.splits == 0 && !initial) {
                 finalize_ties<BITS>(sm, src, count, S, n, rank, bwt_out, ptr_out);
                 tied = true;
@@ -482,6 +559,9 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
             st.pad = 0;
             st.sum_active = sum_active;
             st.sum_active_passes = sum_active_passes;
+            st.cyc_build = (u64)cyc_build;
+            st.cyc_radix = (u64)cyc_radix;
+            st.cyc_rerank = (u64)cyc_rerank;
             a.stats[blk] = st;
         }
         __syncthreads();

@@ -99,6 +99,77 @@ __device__ __forceinline__ u32 block_excl_max(u32 v, u32 *scratch, u32 *total)
     return res;
 }
 
+// Block-wide EXCLUSIVE scan of two independent running maxima packed as (hi:32 | lo:32).
+template <int NT>
+__device__ __forceinline__ u64 block_excl_max2(u64 v, u64 *scratch, u64 *total)
+{
+    constexpr int NWARP = NT / 32;
+    auto mx = [](u64 a, u64 b) -> u64 {
+        u32 ah = (u32)(a >> 32), al = (u32)a, bh = (u32)(b >> 32), bl = (u32)b;
+        return ((u64)max(ah, bh) << 32) | max(al, bl);
+    };
+    u64 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane_id() >= (u32)d) inc = mx(inc, t);
+    }
+    u64 ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane_id() == 0) ex = 0;
+    if (lane_id() == 31) scratch[warp_id()] = inc;
+    __syncthreads();
+    if (warp_id() == 0) {
+        u64 w = lane_id() < NWARP ? scratch[lane_id()] : 0;
+        u64 wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane_id() >= (u32)d) wi = mx(wi, t);
+        }
+        u64 wex = __shfl_up_sync(0xffffffffu, wi, 1);
+        if (lane_id() == 0) wex = 0;
+        scratch[lane_id()] = wex;
+        if (lane_id() == 31) scratch[32] = wi;
+    }
+    __syncthreads();
+    u64 res = mx(scratch[warp_id()], ex);
+    *total = scratch[32];
+    __syncthreads();
+    return res;
+}
+
+// ---- TMA bulk copy (cp.async.bulk, 1-D) + mbarrier helpers --------------------------------
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 template <int NT>
 __device__ __forceinline__ u32 block_sum(u32 v, u32 *scratch)
 {

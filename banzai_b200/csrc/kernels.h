@@ -11,6 +11,8 @@
 #define HUFF_MAX_SYMS 258
 #define HUFF_MAX_TABLES 6
 #define HUFF_REFINEMENTS 4        /* huffman.rs:307 */
+#define BWT_CLUSTER_MAX 16
+#define BWT_CTL_BYTES (3 * 16 * 256 * 4 + 2 * 16 * 4 + 16 * 2 * 4 + 2 * 4 * 4 + 4 + 7 * 4)
 
 namespace bnz {
 
@@ -46,6 +48,7 @@ struct BwtStats {                 // per bzip2 block, written by the sort kernel
     uint32_t pad;
     uint64_t sum_active;          // sum over rounds of records sorted (a_r)
     uint64_t sum_active_passes;   // sum over rounds of a_r * radix passes executed (P_r)
+    uint64_t cyc_build, cyc_radix, cyc_rerank;   // SM cycles spent per phase (thread 0's clock64)
 };
 
 struct BwtArgs {
@@ -60,13 +63,18 @@ struct BwtArgs {
     uint32_t n_blocks;
     uint64_t *ws_rec;             // per CTA: 2 * ws_stride records
     uint32_t *ws_rank;            // per CTA: ws_stride ranks
-    size_t ws_stride;             // >= max block length, multiple of 2
+    size_t ws_stride;             // >= max block length (+ cluster slack), multiple of 16
+    void *ws_ctl;                 // cluster kernel only: per cluster BWT_CTL_BYTES of control state
 };
 
 size_t bwt_smem_bytes(int bits);
 int bwt_passes(int bits);
 cudaError_t bwt_max_ctas(int bits, int *ctas_per_sm);
 cudaError_t bwt_launch(const BwtArgs &a, int bits, int grid, cudaStream_t stream);
+// cluster-cooperative variant (bwt_cluster.cu)
+size_t bwtc_smem_bytes(int threads);
+cudaError_t bwtc_max_clusters(int threads, int C, int *n_clusters);
+cudaError_t bwtc_launch(const BwtArgs &a, int threads, int C, int n_clusters, cudaStream_t stream);
 
 // ---------------------------------------------------------------- K5 MTF + RLE2 (mtf.cu)
 

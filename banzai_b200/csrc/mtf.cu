@@ -25,7 +25,7 @@ namespace mtf {
 
 constexpr int SEG = MTF_SEG;          // bytes per segment
 constexpr int NT1 = 128;              // threads per CTA in M1 / M3
-constexpr int ROW = 260;              // padded list row in shared memory (bank spread)
+constexpr int ROW = 264;              // padded list row in shared memory (8-byte aligned, bank spread)
 
 __device__ __forceinline__ u32 find_block(const u32 *__restrict__ seg_base, u32 n_blocks, u32 seg)
 {
@@ -169,7 +169,11 @@ __global__ void __launch_bounds__(NT1) mtf_apply_kernel(MtfArgs a)
     u8 *dst = a.idx + a.blk_off[b];
     const u32 start = s * SEG, end = min(start + SEG, n);
     u8 *row = rows + tid * ROW;
-    u32 front = row[0];
+    // list positions 0..7 live in a register (byte i = position i); 8..255 stay in the row
+    u64 hq = 0;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) hq = (hq << 8) | row[k];
+    const u64 ONES = 0x0101010101010101ull, HIGH = 0x8080808080808080ull;
 
     for (u32 p = start; p < end; p += 16) {
         u32 w4[4];
@@ -184,19 +188,37 @@ __global__ void __launch_bounds__(NT1) mtf_apply_kernel(MtfArgs a)
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             if (p + j < end) {
-                u32 c = (w4[j >> 2] >> ((j & 3) * 8)) & 0xffu;
-                if (c != front) {
-                    u32 prev = front, k = 1;
-                    for (;;) {
-                        u32 t = row[k];
-                        row[k] = (u8)prev;
-                        prev = t;
-                        if (t == c || k == 255) break;
-                        k++;
+                const u64 c = (w4[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+                const u64 x = hq ^ (c * ONES);
+                const u64 z = (x - ONES) & ~x & HIGH;          // lowest set bit marks the first equal byte
+                u32 k;
+                if (z) {
+                    k = (u32)(__ffsll((long long)z) - 1) >> 3;
+                    const u64 m = (k == 7) ? ~0ull : ((1ull << (8 * (k + 1))) - 1ull);
+                    hq = (hq & ~m) | ((hq << 8) & m) | c;
+                } else {
+                    // deeper than the register head: walk the row 8 entries (one 64-bit word) at a time,
+                    // shifting each word up by one entry and carrying its top entry into the next
+                    u64 carry = hq >> 56;
+                    hq = (hq << 8) | c;
+                    u64 *row64 = reinterpret_cast<u64 *>(row);
+                    k = 255;
+                    for (u32 wi = 1; wi < 32; wi++) {
+                        const u64 wv = row64[wi];
+                        const u64 xx = wv ^ (c * ONES);
+                        const u64 zz = (xx - ONES) & ~xx & HIGH;
+                        if (zz) {
+                            const u32 pb = (u32)(__ffsll((long long)zz) - 1) >> 3;
+                            const u64 m = (pb == 7) ? ~0ull : ((1ull << (8 * (pb + 1))) - 1ull);
+                            row64[wi] = (wv & ~m) | (((wv << 8) | carry) & m);
+                            k = wi * 8 + pb;
+                            break;
+                        }
+                        row64[wi] = (wv << 8) | carry;
+                        carry = wv >> 56;
                     }
-                    front = c;
-                    o4[j >> 2] |= k << ((j & 3) * 8);
                 }
+                o4[j >> 2] |= k << ((j & 3) * 8);
             }
         }
         if (p + 16 <= end) {

@@ -43,17 +43,41 @@ struct DevBuf {
     template <class X> X *as() const { return reinterpret_cast<X *>(p); }
 };
 
+struct PinBuf {                      // grow-only pinned host staging
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class X> X *as() const { return reinterpret_cast<X *>(p); }
+};
+
 struct Device {
     int id = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     // arenas (grown on demand, kept across calls)
-    DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank;
+    DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl;
     DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, rle_blocks, crc_acc;
     DevBuf seg_base, seg_list, seg_cnt, seg_state, num_names, syms, sym_off, sym_len, freqs;
     DevBuf lens, codes, tf, num_tables, num_sel, span_base, hdr, hdr_bits, crc, blk_bits, blk_bitoff,
         total_bits, out;
     cudaEvent_t ev[12] = {};
+    PinBuf h_P, h_oin, h_acc;
     bool crc_tables = false;
     uint32_t launches = 0;
 };
@@ -64,6 +88,9 @@ struct bnz_ctx {
     bnz_stats stats;
     int radix_bits = 8;
     int ctas_per_sm = 0;
+    int bwt_cluster = -1;         // CTAs per bzip2 block (-1: auto, 0/1: single-CTA kernel)
+    int bwt_threads = 512;
+    int bwt_cluster_below = 400;       // auto mode: cluster kernel when a device gets fewer blocks than this
     // cached pinned output buffer handed to the caller by bnz_encode / returned by bnz_free
     uint8_t *out_cache = nullptr;
     size_t out_cache_cap = 0;
@@ -154,7 +181,7 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
         cudaSetDevice(d.id);
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (DevBuf *b : { &d.in, &d.rle, &d.bwt, &d.blk_off, &d.blk_len, &d.ptr, &d.has_byte,
-                           &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ch_lasthead, &d.ch_meta,
+                           &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.ch_lasthead, &d.ch_meta,
                            &d.ch_restsum, &d.ch_oin, &d.ch_P, &d.rle_blocks, &d.crc_acc, &d.seg_base,
                            &d.seg_list, &d.seg_cnt, &d.seg_state, &d.num_names, &d.syms, &d.sym_off,
                            &d.sym_len, &d.freqs, &d.lens, &d.codes, &d.tf, &d.num_tables, &d.num_sel,
@@ -163,6 +190,9 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
             b->release();
         for (cudaEvent_t e : d.ev)
             if (e) cudaEventDestroy(e);
+        d.h_P.release();
+        d.h_oin.release();
+        d.h_acc.release();
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
@@ -175,6 +205,21 @@ extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
     if (!strcmp(key, "bwt_radix_bits")) {
         if (value != 8 && value != 10) return BNZ_EINVAL;
         ctx->radix_bits = (int)value;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "bwt_cluster")) {
+        if (value < -1 || value > BWT_CLUSTER_MAX) return BNZ_EINVAL;
+        ctx->bwt_cluster = (int)value;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "bwt_cluster_below")) {
+        if (value < 0) return BNZ_EINVAL;
+        ctx->bwt_cluster_below = (int)value;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "bwt_threads")) {
+        if (value != 512 && value != 1024) return BNZ_EINVAL;
+        ctx->bwt_threads = (int)value;
         return BNZ_OK;
     }
     if (!strcmp(key, "bwt_ctas_per_sm")) {
@@ -250,17 +295,8 @@ static int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t
                           uint32_t max_len, uint32_t *d_ptr, uint8_t *d_has_byte, BwtStats *d_stats)
 {
     if (n_blocks == 0) return BNZ_OK;
-    int per_sm = 0;
-    CK(ctx, bwt_max_ctas(ctx->radix_bits, &per_sm));
-    if (per_sm <= 0) return fail(ctx, BNZ_ECUDA, "bwt kernel does not fit on an SM");
-    if (ctx->ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->ctas_per_sm);
-    int grid = (int)std::min<uint64_t>((uint64_t)n_blocks, (uint64_t)d.sm_count * per_sm);
-    size_t stride = ((size_t)max_len + 15) & ~(size_t)15;
-    CK(ctx, d.ws_rec.ensure((size_t)grid * 2 * stride * sizeof(uint64_t)));
-    CK(ctx, d.ws_rank.ensure((size_t)grid * stride * sizeof(uint32_t)));
     CK(ctx, d.counters.ensure(256));
     CK(ctx, cudaMemsetAsync(d.counters.p, 0, 256, d.stream));
-
     BwtArgs a;
     a.rle = d_rle;
     a.bwt = d_bwt;
@@ -271,6 +307,41 @@ static int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t
     a.stats = d_stats;
     a.next_block = d.counters.as<uint32_t>();
     a.n_blocks = n_blocks;
+    a.ws_ctl = nullptr;
+
+    // auto: many blocks -> one persistent CTA per block (best aggregate throughput);
+    // few blocks -> one cluster per block so that every SM has work and the randomly accessed
+    // arrays stay in L2 (measured crossover ~400 blocks per device, tools/bwt_blocks_sweep.py)
+    int C = ctx->bwt_cluster;
+    if (C < 0) C = (n_blocks >= (uint32_t)ctx->bwt_cluster_below) ? 0 : (n_blocks <= 40 ? 16 : 8);
+    if (C > 1) {
+        int max_clusters = 0;
+        CK(ctx, bwtc_max_clusters(ctx->bwt_threads, C, &max_clusters));
+        if (max_clusters <= 0) return fail(ctx, BNZ_ECUDA, "bwt cluster shape cannot be scheduled");
+        if (ctx->ctas_per_sm > 0) max_clusters = std::min(max_clusters, ctx->ctas_per_sm * d.sm_count / C);
+        int n_clusters = (int)std::min<uint64_t>((uint64_t)n_blocks, (uint64_t)std::max(1, max_clusters));
+        size_t stride = (((size_t)max_len + 15) & ~(size_t)15) + (size_t)BWT_CLUSTER_MAX * 4096;
+        CK(ctx, d.ws_rec.ensure((size_t)n_clusters * 2 * stride * sizeof(uint64_t)));
+        CK(ctx, d.ws_rank.ensure((size_t)n_clusters * stride * sizeof(uint32_t)));
+        CK(ctx, d.ws_ctl.ensure((size_t)n_clusters * BWT_CTL_BYTES));
+        CK(ctx, cudaMemsetAsync(d_has_byte, 0, (size_t)n_blocks * 256, d.stream));
+        a.ws_rec = d.ws_rec.as<uint64_t>();
+        a.ws_rank = d.ws_rank.as<uint32_t>();
+        a.ws_stride = stride;
+        a.ws_ctl = d.ws_ctl.p;
+        CK(ctx, bwtc_launch(a, ctx->bwt_threads, C, n_clusters, d.stream));
+        d.launches++;
+        return BNZ_OK;
+    }
+
+    int per_sm = 0;
+    CK(ctx, bwt_max_ctas(ctx->radix_bits, &per_sm));
+    if (per_sm <= 0) return fail(ctx, BNZ_ECUDA, "bwt kernel does not fit on an SM");
+    if (ctx->ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->ctas_per_sm);
+    int grid = (int)std::min<uint64_t>((uint64_t)n_blocks, (uint64_t)d.sm_count * per_sm);
+    size_t stride = ((size_t)max_len + 15) & ~(size_t)15;
+    CK(ctx, d.ws_rec.ensure((size_t)grid * 2 * stride * sizeof(uint64_t)));
+    CK(ctx, d.ws_rank.ensure((size_t)grid * stride * sizeof(uint32_t)));
     a.ws_rec = d.ws_rec.as<uint64_t>();
     a.ws_rank = d.ws_rank.as<uint32_t>();
     a.ws_stride = stride;
@@ -340,6 +411,9 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
         s.bwt_rounds_total += st[b].rounds;
         s.bwt_max_rounds = std::max(s.bwt_max_rounds, st[b].rounds);
         s.bwt_tied_blocks += st[b].tied;
+        s.bwt_cyc_build += st[b].cyc_build;
+        s.bwt_cyc_radix += st[b].cyc_radix;
+        s.bwt_cyc_rerank += st[b].cyc_rerank;
         if (stats_out) {
             stats_out[b].n = st[b].n;
             stats_out[b].rounds = st[b].rounds;
@@ -358,11 +432,6 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
 // walk reads <= 2 KiB of it per block).  Leaves the RLE1 images in d.rle and fills `blocks`
 // and `crcs`.
 // ---------------------------------------------------------------------------------------
-
-struct HostScratch {
-    std::vector<uint64_t> P, oin;
-    std::vector<uint32_t> acc;
-};
 
 static int run_rle_device(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const uint8_t *h_in, uint64_t N,
                           int level, std::vector<RleBlock> &blocks, std::vector<uint32_t> &crcs,
@@ -386,14 +455,13 @@ static int run_rle_device(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const ui
                                d.ch_restsum.as<uint32_t>(), d.ch_oin.as<uint64_t>(), d.ch_P.as<uint64_t>(),
                                d.stream));
     d.launches += 2;
-    HostScratch hs;
-    hs.P.resize(n_chunks + 1);
-    hs.oin.resize(n_chunks);
-    CK(ctx, cudaMemcpyAsync(hs.P.data(), d.ch_P.p, (n_chunks + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
-    CK(ctx, cudaMemcpyAsync(hs.oin.data(), d.ch_oin.p, n_chunks * 8, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, d.h_P.ensure((n_chunks + 1) * 8));
+    CK(ctx, d.h_oin.ensure(n_chunks * 8));
+    CK(ctx, cudaMemcpyAsync(d.h_P.p, d.ch_P.p, (n_chunks + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaMemcpyAsync(d.h_oin.p, d.ch_oin.p, n_chunks * 8, cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaStreamSynchronize(d.stream));
 
-    if (rle_walk_cuts(h_in, N, level, hs.P.data(), hs.oin.data(), n_chunks, blocks) != 0)
+    if (rle_walk_cuts(h_in, N, level, d.h_P.as<uint64_t>(), d.h_oin.as<uint64_t>(), n_chunks, blocks) != 0)
         return fail(ctx, BNZ_EINTERNAL, "RLE1 cut walk failed");
     const size_t nb = blocks.size();
     uint64_t total = blocks.back().rle_off + ((blocks.back().n + 15) & ~15ull);
@@ -407,11 +475,11 @@ static int run_rle_device(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const ui
                             d.rle_blocks.as<RleBlock>(), (uint32_t)nb, d.rle.as<uint8_t>(),
                             d.crc_acc.as<uint32_t>(), d.stream));
     d.launches += 2;
-    hs.acc.resize(nb);
-    CK(ctx, cudaMemcpyAsync(hs.acc.data(), d.crc_acc.p, nb * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, d.h_acc.ensure(nb * 4));
+    CK(ctx, cudaMemcpyAsync(d.h_acc.p, d.crc_acc.p, nb * 4, cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaStreamSynchronize(d.stream));
     crcs.resize(nb);
-    for (size_t b = 0; b < nb; b++) crcs[b] = crc_finalize(hs.acc[b], blocks[b].c - blocks[b].s);
+    for (size_t b = 0; b < nb; b++) crcs[b] = crc_finalize(d.h_acc.as<uint32_t>()[b], blocks[b].c - blocks[b].s);
     return BNZ_OK;
 }
 
@@ -808,6 +876,9 @@ static int encode_single(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in_
         st.bwt_rounds_total += bst[b].rounds;
         st.bwt_max_rounds = std::max(st.bwt_max_rounds, bst[b].rounds);
         st.bwt_tied_blocks += bst[b].tied;
+        st.bwt_cyc_build += bst[b].cyc_build;
+        st.bwt_cyc_radix += bst[b].cyc_radix;
+        st.bwt_cyc_rerank += bst[b].cyc_rerank;
     }
     st.bwt_algorithmic_bytes = 9 * st.bwt_n + 16 * st.bwt_sum_active_passes + 36 * st.bwt_sum_active;
     return BNZ_OK;

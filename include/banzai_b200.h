@@ -47,7 +47,9 @@ BNZ_API const char *bnz_strerror(int code);
 /* human-readable detail of the last failing call on this context ("" if none) */
 BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
 
-/* tunables (call before encoding). key: "bwt_radix_bits" (8|10), "bwt_ctas_per_sm" (0=auto) */
+/* tunables (call before encoding). keys: "bwt_cluster" (-1 auto | 0 one CTA per block | 2..16 CTAs
+ * per block), "bwt_cluster_below" (auto threshold in blocks), "bwt_threads" (512|1024, cluster
+ * kernel), "bwt_radix_bits" (8|10, one-CTA kernel), "bwt_ctas_per_sm" (0 = auto) */
 BNZ_API int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value);
 
 /* ---- the hot path --------------------------------------------------------------------
@@ -107,6 +109,7 @@ typedef struct bnz_stats {
     uint32_t bwt_tied_blocks;
     uint64_t bwt_rounds_total;
     uint64_t bwt_algorithmic_bytes;  /* n + 8n + sum a_r * (16 P_r + 36)   */
+    uint64_t bwt_cyc_build, bwt_cyc_radix, bwt_cyc_rerank;   /* SM cycles per phase, summed over blocks */
     uint64_t h2d_bytes, d2h_bytes;
 } bnz_stats;
 BNZ_API int bnz_get_stats(const bnz_ctx *ctx, bnz_stats *out);

@@ -22,15 +22,24 @@ def ctx():
     c.close()
 
 
+MODES = {8: [("cluster", 8), ("cluster", 16), ("cluster", 2), ("single", 8)], 10: [("single", 10)]}
+
+
 def _check(ctx, blocks, level=9, bits=(8, 10)):
-    for b in bits:
-        ctx.set("bwt_radix_bits", b)
+    modes = [m for b in bits for m in MODES[b]]
+    for kind, val in modes:
+        if kind == "cluster":
+            ctx.set("bwt_cluster", val)
+        else:
+            ctx.set("bwt_cluster", 0)
+            ctx.set("bwt_radix_bits", val)
         got = ctx.stage_bwt(blocks, level, with_stats=True)
         for blk, (bw, ptr, has, st) in zip(blocks, got):
             ebw, eptr, ehas = O.bwt(blk)
             assert ptr == eptr, (len(blk), st)
             assert bytes(bw) == bytes(ebw), (len(blk), st)
             assert (has == ehas).all()
+    ctx.set("bwt_cluster", -1)
     return got
 
 
