@@ -520,6 +520,14 @@ cudaError_t huff_pack_launch(const HuffArgs &a, cudaStream_t st, uint32_t *launc
     return cudaGetLastError();
 }
 
+cudaError_t huff_rescan_launch(const HuffArgs &a, cudaStream_t st, uint32_t *launches)
+{
+    if (a.n_blocks == 0) return cudaSuccess;
+    huff::huff_scan_kernel<<<1, 1024, 0, st>>>(a);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 uint32_t huff_groups_per_span() { return huff::GPC; }
 
 }  // namespace bnz

@@ -33,9 +33,9 @@ uint32_t crc_finalize(uint32_t acc, uint64_t len);
 cudaError_t rle_summary_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks, uint64_t *d_lasthead,
                                uint32_t *d_meta, uint32_t *d_restsum, uint64_t *d_oin, uint64_t *d_P,
                                cudaStream_t st);
-cudaError_t rle_emit_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks, const uint64_t *d_oin,
-                            const uint64_t *d_P, const RleBlock *d_blocks, uint32_t n_blocks, uint8_t *d_out,
-                            uint32_t *d_crc_acc, cudaStream_t st);
+cudaError_t rle_emit_launch(const uint8_t *d_in, uint64_t N, uint64_t c_begin, uint64_t c_end,
+                            const uint64_t *d_oin, const uint64_t *d_P, const RleBlock *d_blocks,
+                            uint32_t n_blocks, uint8_t *d_out, uint32_t *d_crc_acc, cudaStream_t st);
 int rle_walk_cuts(const uint8_t *in, uint64_t N, int level, const uint64_t *P, const uint64_t *o_in,
                   uint64_t n_chunks, std::vector<RleBlock> &blocks);
 
@@ -131,6 +131,7 @@ struct HuffArgs {
 };
 cudaError_t huff_launch(const HuffArgs &a, uint32_t total_spans, cudaStream_t st, uint32_t *launches);
 cudaError_t huff_pack_launch(const HuffArgs &a, cudaStream_t st, uint32_t *launches);
+cudaError_t huff_rescan_launch(const HuffArgs &a, cudaStream_t st, uint32_t *launches);
 uint32_t huff_groups_per_span();
 
 }  // namespace bnz

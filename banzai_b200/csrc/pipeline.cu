@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 #include <string.h>
 #include <stdlib.h>
@@ -97,18 +98,26 @@ struct bnz_ctx {
     bool out_cache_lent = false;
 };
 
+// worker threads of a multi-device encode record their error text in their own string
+static thread_local std::string *t_err_sink = nullptr;
+static void set_err(bnz_ctx *ctx, const std::string &msg)
+{
+    if (t_err_sink) *t_err_sink = msg;
+    else if (ctx) ctx->err = msg;
+}
+
 #define CK(ctx, call)                                                                          \
     do {                                                                                       \
         cudaError_t e__ = (call);                                                              \
         if (e__ != cudaSuccess) {                                                              \
-            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
+            set_err((ctx), std::string(#call) + ": " + cudaGetErrorString(e__));               \
             return (e__ == cudaErrorMemoryAllocation) ? BNZ_ENOMEM : BNZ_ECUDA;                \
         }                                                                                      \
     } while (0)
 
 static int fail(bnz_ctx *ctx, int code, const std::string &msg)
 {
-    if (ctx) ctx->err = msg;
+    set_err(ctx, msg);
     return code;
 }
 
@@ -433,18 +442,13 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
 // and `crcs`.
 // ---------------------------------------------------------------------------------------
 
-static int run_rle_device(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const uint8_t *h_in, uint64_t N,
-                          int level, std::vector<RleBlock> &blocks, std::vector<uint32_t> &crcs,
-                          uint64_t *rle_total)
+// K1 part 1 on one device: chunk tables -> host -> cut walk.  Leaves P / o_in in d.h_P / d.h_oin
+// (host, pinned) and in d.ch_P / d.ch_oin (device).
+static int rle_plan(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const uint8_t *h_in, uint64_t N, int level,
+                    std::vector<RleBlock> &blocks)
 {
     blocks.clear();
-    crcs.clear();
-    *rle_total = 0;
     if (N == 0) return BNZ_OK;
-    if (!d.crc_tables) {
-        CK(ctx, crc_upload_tables());
-        d.crc_tables = true;
-    }
     const uint64_t n_chunks = (N + RLE_CHUNK - 1) / RLE_CHUNK;
     CK(ctx, d.ch_lasthead.ensure(n_chunks * 8));
     CK(ctx, d.ch_meta.ensure(n_chunks * 4));
@@ -460,20 +464,37 @@ static int run_rle_device(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const ui
     CK(ctx, cudaMemcpyAsync(d.h_P.p, d.ch_P.p, (n_chunks + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaMemcpyAsync(d.h_oin.p, d.ch_oin.p, n_chunks * 8, cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaStreamSynchronize(d.stream));
-
     if (rle_walk_cuts(h_in, N, level, d.h_P.as<uint64_t>(), d.h_oin.as<uint64_t>(), n_chunks, blocks) != 0)
         return fail(ctx, BNZ_EINTERNAL, "RLE1 cut walk failed");
+    return BNZ_OK;
+}
+
+// K1 part 2 + K2 on one device for a contiguous range of blocks.  `blocks` holds the range with
+// rle_off rebased to 0; in_base / oin_base / P_base are device pointers indexed by GLOBAL input
+// position / chunk (rebased by the caller when only a sub-range is resident).
+static int rle_emit_shard(bnz_ctx *ctx, Device &d, const uint8_t *in_base, uint64_t N, const uint64_t *oin_base,
+                          const uint64_t *P_base, const std::vector<RleBlock> &blocks, std::vector<uint32_t> &crcs,
+                          uint64_t *rle_total)
+{
+    crcs.clear();
+    *rle_total = 0;
     const size_t nb = blocks.size();
-    uint64_t total = blocks.back().rle_off + ((blocks.back().n + 15) & ~15ull);
+    if (nb == 0) return BNZ_OK;
+    if (!d.crc_tables) {
+        CK(ctx, crc_upload_tables());
+        d.crc_tables = true;
+    }
+    const uint64_t total = blocks.back().rle_off + ((blocks.back().n + 15) & ~15ull);
     *rle_total = total;
+    const uint64_t c_begin = blocks.front().s / RLE_CHUNK;
+    const uint64_t c_end = (blocks.back().c + RLE_CHUNK - 1) / RLE_CHUNK;
     CK(ctx, d.rle_blocks.ensure(nb * sizeof(RleBlock)));
     CK(ctx, d.crc_acc.ensure(nb * 4));
     CK(ctx, d.rle.ensure(total));
     CK(ctx, cudaMemcpyAsync(d.rle_blocks.p, blocks.data(), nb * sizeof(RleBlock), cudaMemcpyHostToDevice, d.stream));
     CK(ctx, cudaMemsetAsync(d.crc_acc.p, 0, nb * 4, d.stream));
-    CK(ctx, rle_emit_launch(d_in, N, n_chunks, d.ch_oin.as<uint64_t>(), d.ch_P.as<uint64_t>(),
-                            d.rle_blocks.as<RleBlock>(), (uint32_t)nb, d.rle.as<uint8_t>(),
-                            d.crc_acc.as<uint32_t>(), d.stream));
+    CK(ctx, rle_emit_launch(in_base, N, c_begin, c_end, oin_base, P_base, d.rle_blocks.as<RleBlock>(), (uint32_t)nb,
+                            d.rle.as<uint8_t>(), d.crc_acc.as<uint32_t>(), d.stream));
     d.launches += 2;
     CK(ctx, d.h_acc.ensure(nb * 4));
     CK(ctx, cudaMemcpyAsync(d.h_acc.p, d.crc_acc.p, nb * 4, cudaMemcpyDeviceToHost, d.stream));
@@ -481,6 +502,17 @@ static int run_rle_device(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const ui
     crcs.resize(nb);
     for (size_t b = 0; b < nb; b++) crcs[b] = crc_finalize(d.h_acc.as<uint32_t>()[b], blocks[b].c - blocks[b].s);
     return BNZ_OK;
+}
+
+static int run_rle_device(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const uint8_t *h_in, uint64_t N,
+                          int level, std::vector<RleBlock> &blocks, std::vector<uint32_t> &crcs,
+                          uint64_t *rle_total)
+{
+    crcs.clear();
+    *rle_total = 0;
+    int rc = rle_plan(ctx, d, d_in, h_in, N, level, blocks);
+    if (rc != BNZ_OK || blocks.empty()) return rc;
+    return rle_emit_shard(ctx, d, d_in, N, d.ch_oin.as<uint64_t>(), d.ch_P.as<uint64_t>(), blocks, crcs, rle_total);
 }
 
 extern "C" int bnz_stage_rle1(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int level, uint64_t *blk_in_off,
@@ -792,45 +824,43 @@ static void put_bits_host(uint8_t *buf, uint64_t bitpos, uint64_t value, int nbi
         if ((value >> i) & 1) buf[bitpos >> 3] |= (uint8_t)(0x80u >> (bitpos & 7));
 }
 
-// Encodes on device 0.  d_in: device copy of the input (uploaded here when null), h_in: host
-// copy.  The finished stream is left in d.out (bytes [0, *out_len)) — header and footer are
-// patched on the host side by the callers.
-static int encode_single(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in_given, size_t N, int level,
-                         std::vector<uint32_t> &crcs, uint64_t *total_bits_out)
-{
-    Device &d = ctx->devs[0];
-    bnz_stats &st = ctx->stats;
-    CK(ctx, cudaSetDevice(d.id));
-    d.launches = 0;
-    const uint8_t *d_in = d_in_given;
-    CK(ctx, cudaEventRecord(d.ev[0], d.stream));
-    if (!d_in) {
-        CK(ctx, d.in.ensure(N + 64));
-        CK(ctx, cudaMemcpyAsync(d.in.p, h_in, N, cudaMemcpyHostToDevice, d.stream));
-        d_in = d.in.as<uint8_t>();
-        st.h2d_bytes += N;
-    }
-    CK(ctx, cudaEventRecord(d.ev[1], d.stream));
+// One device's share of a bnz_encode call: a contiguous range of blocks.
+struct Shard {
+    Device *d = nullptr;
+    std::vector<RleBlock> blocks;      // rle_off rebased to this device's rle buffer
+    std::vector<uint32_t> crcs;
+    std::vector<BwtStats> bst;
+    Batch bt;
+    HuffArgs ha;
+    uint64_t block_bits = 0;           // sum of the shard's block bit lengths
+    uint64_t bit_base = 0;             // global bit offset of the shard's first block
+    int rc = BNZ_OK;
+    std::string err;
+};
 
-    // K1/K2
-    std::vector<RleBlock> blocks;
+// K1 emit .. K7 + headers for one shard; ends with a host sync that yields block_bits.
+// in_base/oin_base/P_base: see rle_emit_shard.
+static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t N, const uint64_t *oin_base,
+                       const uint64_t *P_base, int level)
+{
+    Device &d = *sh.d;
     uint64_t rle_total = 0;
-    int rc = run_rle_device(ctx, d, d_in, h_in, N, level, blocks, crcs, &rle_total);
+    int rc = rle_emit_shard(ctx, d, in_base, N, oin_base, P_base, sh.blocks, sh.crcs, &rle_total);
     if (rc != BNZ_OK) return rc;
     CK(ctx, cudaEventRecord(d.ev[2], d.stream));
-    const uint32_t nb = (uint32_t)blocks.size();
-    Batch bt;
+    const uint32_t nb = (uint32_t)sh.blocks.size();
+    Batch &bt = sh.bt;
     bt.blk_off.resize(nb);
     bt.blk_len.resize(nb);
     for (uint32_t b = 0; b < nb; b++) {
-        bt.blk_off[b] = blocks[b].rle_off;
-        bt.blk_len[b] = blocks[b].n;
+        bt.blk_off[b] = sh.blocks[b].rle_off;
+        bt.blk_len[b] = sh.blocks[b].n;
     }
     bt.bytes_total = rle_total;
     bt.build();
     rc = upload_batch(ctx, d, bt);
     if (rc != BNZ_OK) return rc;
-    CK(ctx, upload(d.crc, crcs, d.stream));
+    CK(ctx, upload(d.crc, sh.crcs, d.stream));
 
     // K3/K4
     CK(ctx, d.bwt.ensure(rle_total));
@@ -843,61 +873,75 @@ static int encode_single(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in_
     if (rc != BNZ_OK) return rc;
     CK(ctx, cudaEventRecord(d.ev[3], d.stream));
 
-    // K5 (the RLE1 images are dead now: reuse their buffer for the MTF index bytes)
+    // K5 (the RLE1 images are dead now: their buffer holds the MTF index bytes)
     rc = run_mtf_device(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>());
     if (rc != BNZ_OK) return rc;
     CK(ctx, cudaEventRecord(d.ev[4], d.stream));
 
-    // K6/K7 + headers + offsets
-    HuffArgs ha;
-    rc = run_huff_model_device(ctx, d, bt, level, 1, 32, 0, ha);
+    // K6/K7 + headers + block bit lengths
+    rc = run_huff_model_device(ctx, d, bt, level, 1, 0, 0, sh.ha);
     if (rc != BNZ_OK) return rc;
-    uint64_t total_bits = 0;
-    std::vector<BwtStats> bst(nb);
-    CK(ctx, cudaMemcpyAsync(&total_bits, d.total_bits.p, 8, cudaMemcpyDeviceToHost, d.stream));
-    CK(ctx, cudaMemcpyAsync(bst.data(), d.bwt_stats.p, (size_t)nb * sizeof(BwtStats), cudaMemcpyDeviceToHost, d.stream));
+    sh.bst.resize(nb);
+    CK(ctx, cudaMemcpyAsync(&sh.block_bits, d.total_bits.p, 8, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaMemcpyAsync(sh.bst.data(), d.bwt_stats.p, (size_t)nb * sizeof(BwtStats), cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaEventRecord(d.ev[5], d.stream));
     CK(ctx, cudaStreamSynchronize(d.stream));
-
-    // K8
-    const size_t out_bytes = (size_t)((total_bits + 80 + 7) / 8);
-    CK(ctx, d.out.ensure(out_bytes + 64));
-    CK(ctx, cudaMemsetAsync(d.out.p, 0, ((out_bytes + 63) & ~(size_t)63), d.stream));
-    ha.out_words = d.out.as<uint32_t>();
-    CK(ctx, huff_pack_launch(ha, d.stream, &d.launches));
-    CK(ctx, cudaEventRecord(d.ev[6], d.stream));
-    *total_bits_out = total_bits;
-
-    st.n_blocks = nb;
-    for (uint32_t b = 0; b < nb; b++) {
-        st.bwt_n += bst[b].n;
-        st.bwt_sum_active += bst[b].sum_active;
-        st.bwt_sum_active_passes += bst[b].sum_active_passes;
-        st.bwt_rounds_total += bst[b].rounds;
-        st.bwt_max_rounds = std::max(st.bwt_max_rounds, bst[b].rounds);
-        st.bwt_tied_blocks += bst[b].tied;
-        st.bwt_cyc_build += bst[b].cyc_build;
-        st.bwt_cyc_radix += bst[b].cyc_radix;
-        st.bwt_cyc_rerank += bst[b].cyc_rerank;
-    }
-    st.bwt_algorithmic_bytes = 9 * st.bwt_n + 16 * st.bwt_sum_active_passes + 36 * st.bwt_sum_active;
     return BNZ_OK;
 }
 
-static void finish_stats(bnz_ctx *ctx, Device &d, bool have_d2h)
+// K8 for one shard once its global bit offset is known.  The shard's bits land in d.out such
+// that d.out word 0 is global word (bit_base / 32).
+static int shard_pack(bnz_ctx *ctx, Shard &sh, size_t *out_bytes)
+{
+    Device &d = *sh.d;
+    const uint64_t local_base = sh.bit_base & 31;
+    const size_t bytes = (size_t)((local_base + sh.block_bits + 31) / 32) * 4;
+    *out_bytes = bytes;
+    CK(ctx, d.out.ensure(bytes + 256));
+    CK(ctx, cudaMemsetAsync(d.out.p, 0, ((bytes + 127) & ~(size_t)63), d.stream));
+    sh.ha.out_words = d.out.as<uint32_t>();
+    sh.ha.bit_base = local_base;
+    CK(ctx, huff_rescan_launch(sh.ha, d.stream, &d.launches));
+    CK(ctx, huff_pack_launch(sh.ha, d.stream, &d.launches));
+    CK(ctx, cudaEventRecord(d.ev[6], d.stream));
+    return BNZ_OK;
+}
+
+static void add_stats(bnz_stats &st, const Shard &sh)
+{
+    st.n_blocks += (uint32_t)sh.blocks.size();
+    for (const BwtStats &b : sh.bst) {
+        st.bwt_n += b.n;
+        st.bwt_sum_active += b.sum_active;
+        st.bwt_sum_active_passes += b.sum_active_passes;
+        st.bwt_rounds_total += b.rounds;
+        st.bwt_max_rounds = std::max(st.bwt_max_rounds, b.rounds);
+        st.bwt_tied_blocks += b.tied;
+        st.bwt_cyc_build += b.cyc_build;
+        st.bwt_cyc_radix += b.cyc_radix;
+        st.bwt_cyc_rerank += b.cyc_rerank;
+    }
+    st.bwt_algorithmic_bytes = 9 * st.bwt_n + 16 * st.bwt_sum_active_passes + 36 * st.bwt_sum_active;
+    st.kernel_launches += sh.d->launches;
+}
+
+static void finish_stats(bnz_ctx *ctx, std::vector<Shard> &shards, bool have_d2h)
 {
     bnz_stats &st = ctx->stats;
-    auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, d.ev[a], d.ev[b]); return ms; };
-    st.h2d_ms = el(0, 1);
-    st.rle_ms = el(1, 2);
-    st.bwt_ms = el(2, 3);
-    st.mtf_ms = el(3, 4);
-    st.huff_ms = el(4, 5);
-    st.pack_ms = el(5, 6);
-    st.d2h_ms = have_d2h ? el(6, 7) : 0.f;
-    st.total_ms = el(0, have_d2h ? 7 : 6);
-    st.kernel_launches = d.launches;
-    st.n_devices = 1;
+    for (Shard &sh : shards) {
+        Device &d = *sh.d;
+        cudaSetDevice(d.id);
+        auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, d.ev[a], d.ev[b]); return ms; };
+        st.h2d_ms = std::max(st.h2d_ms, el(0, 1));
+        st.rle_ms = std::max(st.rle_ms, el(1, 2));
+        st.bwt_ms = std::max(st.bwt_ms, el(2, 3));
+        st.mtf_ms = std::max(st.mtf_ms, el(3, 4));
+        st.huff_ms = std::max(st.huff_ms, el(4, 5));
+        st.pack_ms = std::max(st.pack_ms, el(5, 6));
+        if (have_d2h) st.d2h_ms = std::max(st.d2h_ms, el(6, 7));
+        st.total_ms = std::max(st.total_ms, el(0, have_d2h ? 7 : 6));
+    }
+    st.n_devices = (uint32_t)shards.size();
     st.bwt_radix_bits = (uint32_t)ctx->radix_bits;
 }
 
@@ -906,6 +950,125 @@ static uint32_t fold_stream_crc(const std::vector<uint32_t> &crcs)       // lib.
     uint32_t s = 0;
     for (uint32_t c : crcs) s = c ^ ((s << 1) | (s >> 31));
     return s;
+}
+
+static int ensure_out_cache(bnz_ctx *ctx, size_t nbytes)
+{
+    if (ctx->out_cache_cap < nbytes + 16) {
+        if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
+        ctx->out_cache = nullptr;
+        ctx->out_cache_cap = 0;
+        size_t want = nbytes + nbytes / 4 + 4096;
+        CK(ctx, cudaHostAlloc((void **)&ctx->out_cache, want, cudaHostAllocPortable));
+        ctx->out_cache_cap = want;
+    }
+    return BNZ_OK;
+}
+
+// contiguous block ranges with ~equal RLE1 bytes per device
+static std::vector<uint32_t> split_blocks(const std::vector<RleBlock> &blocks, size_t n_dev)
+{
+    std::vector<uint32_t> cut(n_dev + 1, 0);
+    uint64_t total = 0;
+    for (const RleBlock &b : blocks) total += b.n;
+    uint64_t acc = 0;
+    size_t g = 1;
+    for (uint32_t i = 0; i < blocks.size() && g < n_dev; i++) {
+        acc += blocks[i].n;
+        while (g < n_dev && acc * n_dev >= total * g) cut[g++] = i + 1;
+    }
+    for (; g <= n_dev; g++) cut[g] = (uint32_t)blocks.size();
+    return cut;
+}
+
+// The whole path.  h_in: host input; d_in0: optional device copy already resident on device 0
+// (single-device contexts only).  Leaves every shard's bits in its device's d.out and returns
+// the stream layout; the callers move the bytes.
+static int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, size_t N, int level,
+                      std::vector<Shard> &shards, std::vector<uint32_t> &crcs, uint64_t *total_bits)
+{
+    Device &d0 = ctx->devs[0];
+    bnz_stats &st = ctx->stats;
+    for (Device &d : ctx->devs) d.launches = 0;
+    CK(ctx, cudaSetDevice(d0.id));
+    CK(ctx, cudaEventRecord(d0.ev[0], d0.stream));
+    const uint8_t *d_in = d_in0;
+    if (!d_in) {
+        CK(ctx, d0.in.ensure(N + 64));
+        CK(ctx, cudaMemcpyAsync(d0.in.p, h_in, N, cudaMemcpyHostToDevice, d0.stream));
+        d_in = d0.in.as<uint8_t>();
+        st.h2d_bytes += N;
+    }
+    CK(ctx, cudaEventRecord(d0.ev[1], d0.stream));
+
+    std::vector<RleBlock> blocks;
+    int rc = rle_plan(ctx, d0, d_in, h_in, N, level, blocks);
+    if (rc != BNZ_OK) return rc;
+
+    const size_t n_dev = std::min(ctx->devs.size(), std::max<size_t>(1, blocks.size()));
+    std::vector<uint32_t> cut = split_blocks(blocks, n_dev);
+    shards.assign(n_dev, Shard());
+    for (size_t g = 0; g < n_dev; g++) {
+        Shard &sh = shards[g];
+        sh.d = &ctx->devs[g];
+        sh.blocks.assign(blocks.begin() + cut[g], blocks.begin() + cut[g + 1]);
+        const uint64_t off0 = sh.blocks.empty() ? 0 : sh.blocks.front().rle_off;
+        for (RleBlock &b : sh.blocks) b.rle_off -= off0;
+    }
+
+    const uint64_t *h_P = d0.h_P.as<uint64_t>(), *h_oin = d0.h_oin.as<uint64_t>();
+    auto work = [&](size_t g) -> int {
+        Shard &sh = shards[g];
+        Device &d = *sh.d;
+        if (sh.blocks.empty()) return BNZ_OK;
+        CK(ctx, cudaSetDevice(d.id));
+        if (g == 0) return shard_model(ctx, sh, d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
+        // other devices: make their input range and chunk tables resident
+        CK(ctx, cudaEventRecord(d.ev[0], d.stream));
+        const uint64_t c0 = sh.blocks.front().s / RLE_CHUNK;
+        const uint64_t c1 = (sh.blocks.back().c + RLE_CHUNK - 1) / RLE_CHUNK;
+        const uint64_t a = c0 ? c0 * RLE_CHUNK - 16 : 0;
+        const uint64_t b = std::min<uint64_t>(N, c1 * RLE_CHUNK + 16);
+        CK(ctx, d.in.ensure(b - a + 64));
+        CK(ctx, cudaMemcpyAsync(d.in.p, h_in + a, b - a, cudaMemcpyHostToDevice, d.stream));
+        CK(ctx, d.ch_oin.ensure((c1 - c0 + 1) * 8));
+        CK(ctx, d.ch_P.ensure((c1 - c0 + 2) * 8));
+        CK(ctx, cudaMemcpyAsync(d.ch_oin.p, h_oin + c0, (c1 - c0) * 8, cudaMemcpyHostToDevice, d.stream));
+        CK(ctx, cudaMemcpyAsync(d.ch_P.p, h_P + c0, (c1 - c0 + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+        CK(ctx, cudaEventRecord(d.ev[1], d.stream));
+        return shard_model(ctx, sh, d.in.as<uint8_t>() - a, N, d.ch_oin.as<uint64_t>() - c0, d.ch_P.as<uint64_t>() - c0, level);
+    };
+
+    if (n_dev == 1) {
+        rc = work(0);
+        if (rc != BNZ_OK) return rc;
+    } else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < n_dev; g++)
+            th.emplace_back([&, g]() {
+                t_err_sink = &shards[g].err;
+                shards[g].rc = work(g);
+                t_err_sink = nullptr;
+            });
+        for (std::thread &t : th) t.join();
+        for (Shard &sh : shards)
+            if (sh.rc != BNZ_OK) {
+                ctx->err = sh.err;
+                return sh.rc;
+            }
+    }
+
+    // bit offsets of the shards (blocks are concatenated at bit granularity, lib.rs:101-126 + out.rs)
+    uint64_t bits = 32;
+    crcs.clear();
+    for (Shard &sh : shards) {
+        sh.bit_base = bits;
+        bits += sh.block_bits;
+        crcs.insert(crcs.end(), sh.crcs.begin(), sh.crcs.end());
+    }
+    *total_bits = bits;
+    for (Shard &sh : shards) add_stats(st, sh);
+    return BNZ_OK;
 }
 
 extern "C" int bnz_encode(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int level, uint8_t **out,
@@ -920,33 +1083,60 @@ extern "C" int bnz_encode(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int le
     if (ctx->out_cache_lent) return fail(ctx, BNZ_EINVAL, "previous output not released with bnz_free");
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.in_bytes = in_len;
-    Device &d = ctx->devs[0];
-    CK(ctx, cudaSetDevice(d.id));
 
     uint64_t total_bits = 32;
     std::vector<uint32_t> crcs;
+    std::vector<Shard> shards;
     if (in_len > 0) {
-        int rc = encode_single(ctx, in, nullptr, in_len, level, crcs, &total_bits);
+        int rc = encode_all(ctx, in, nullptr, in_len, level, shards, crcs, &total_bits);
         if (rc != BNZ_OK) return rc;
     }
     const size_t nbytes = (size_t)((total_bits + 80 + 7) / 8);
-    if (ctx->out_cache_cap < nbytes + 16) {
-        if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
-        ctx->out_cache = nullptr;
-        ctx->out_cache_cap = 0;
-        size_t want = nbytes + nbytes / 4 + 4096;
-        CK(ctx, cudaHostAlloc((void **)&ctx->out_cache, want, cudaHostAllocPortable));
-        ctx->out_cache_cap = want;
-    }
+    int rc = ensure_out_cache(ctx, nbytes + 8);
+    if (rc != BNZ_OK) return rc;
     uint8_t *o = ctx->out_cache;
+
     if (in_len > 0) {
-        CK(ctx, cudaMemcpyAsync(o, d.out.p, nbytes, cudaMemcpyDeviceToHost, d.stream));
-        CK(ctx, cudaEventRecord(d.ev[7], d.stream));
-        CK(ctx, cudaStreamSynchronize(d.stream));
-        ctx->stats.d2h_bytes += nbytes;
-        finish_stats(ctx, d, true);
+        // every shard packs at its bit phase and copies straight into the output; a word shared
+        // by two shards is OR-ed on the host afterwards
+        std::vector<uint32_t> first_word(shards.size(), 0);
+        for (size_t g = 0; g < shards.size(); g++) {
+            Shard &sh = shards[g];
+            if (sh.blocks.empty()) continue;
+            Device &d = *sh.d;
+            CK(ctx, cudaSetDevice(d.id));
+            size_t bytes = 0;
+            rc = shard_pack(ctx, sh, &bytes);
+            if (rc != BNZ_OK) return rc;
+            const size_t w0 = (size_t)(sh.bit_base >> 5) * 4;
+            if (g == 0) {
+                CK(ctx, cudaMemcpyAsync(o + w0, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
+            } else {
+                CK(ctx, cudaMemcpyAsync(&first_word[g], d.out.p, 4, cudaMemcpyDeviceToHost, d.stream));
+                if (bytes > 4)
+                    CK(ctx, cudaMemcpyAsync(o + w0 + 4, d.out.as<uint8_t>() + 4, bytes - 4, cudaMemcpyDeviceToHost, d.stream));
+            }
+            CK(ctx, cudaEventRecord(d.ev[7], d.stream));
+            ctx->stats.d2h_bytes += bytes;
+        }
+        for (Shard &sh : shards) {
+            if (sh.blocks.empty()) continue;
+            CK(ctx, cudaSetDevice(sh.d->id));
+            CK(ctx, cudaStreamSynchronize(sh.d->stream));
+        }
+        // zero the tail the devices did not write, then merge the shared words
+        const size_t written = (size_t)((total_bits + 31) / 32) * 4;
+        if (written < nbytes + 8) memset(o + written, 0, nbytes + 8 - written);
+        for (size_t g = 1; g < shards.size(); g++) {
+            if (shards[g].blocks.empty()) continue;
+            uint8_t *w = o + (size_t)(shards[g].bit_base >> 5) * 4;
+            const uint8_t *f = reinterpret_cast<const uint8_t *>(&first_word[g]);
+            if ((shards[g].bit_base & 31) == 0) memcpy(w, f, 4);
+            else for (int k = 0; k < 4; k++) w[k] |= f[k];
+        }
+        finish_stats(ctx, shards, true);
     } else {
-        memset(o, 0, nbytes);
+        memset(o, 0, nbytes + 8);
     }
     // stream header (lib.rs:18-22), footer (lib.rs:66-70), zero padding (out.rs:22-28)
     o[0] = 0x42; o[1] = 0x5A; o[2] = 0x68; o[3] = (uint8_t)('0' + level);
@@ -973,32 +1163,39 @@ extern "C" int bnz_encode_device(bnz_ctx *ctx, const void *d_in, const uint8_t *
     *out_len = 0;
     if (level < 1 || level > 9) return fail(ctx, BNZ_EINVAL, "level must be in 1..=9 (lib/lib.rs:89)");
     if (in_len == 0 || !d_in || !h_in) return BNZ_EINVAL;
+    if (ctx->devs.size() != 1) return fail(ctx, BNZ_EINVAL, "bnz_encode_device needs a single-device context");
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.in_bytes = in_len;
     Device &d = ctx->devs[0];
     uint64_t total_bits = 32;
     std::vector<uint32_t> crcs;
-    int rc = encode_single(ctx, h_in, (const uint8_t *)d_in, in_len, level, crcs, &total_bits);
+    std::vector<Shard> shards;
+    int rc = encode_all(ctx, h_in, (const uint8_t *)d_in, in_len, level, shards, crcs, &total_bits);
+    if (rc != BNZ_OK) return rc;
+    size_t bytes = 0;
+    rc = shard_pack(ctx, shards[0], &bytes);
     if (rc != BNZ_OK) return rc;
     const size_t nbytes = (size_t)((total_bits + 80 + 7) / 8);
     if (nbytes > d_out_cap) return fail(ctx, BNZ_EINVAL, "d_out_cap too small");
-    // header / footer patched into the device stream: 4 + 10(+1) bytes
+    // assemble the stream in d_out: 4 header bytes, the packed blocks (d.out word 0 is global
+    // word 1 because shard 0 starts at bit 32), then the footer patched over the last partial byte
     uint8_t tail[16] = { 0 };
     const uint64_t tb = total_bits & 7;
+    const size_t last = (size_t)(total_bits >> 3);          // global byte index of the partial byte
     uint8_t lastbyte = 0;
-    if (tb) CK(ctx, cudaMemcpyAsync(&lastbyte, d.out.as<uint8_t>() + (total_bits >> 3), 1, cudaMemcpyDeviceToHost, d.stream));
+    if (tb) CK(ctx, cudaMemcpyAsync(&lastbyte, d.out.as<uint8_t>() + (last - 4), 1, cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaStreamSynchronize(d.stream));
     tail[0] = lastbyte;
     put_bits_host(tail, tb, 0x177245385090ull, 48);
     put_bits_host(tail, tb + 48, fold_stream_crc(crcs), 32);
     const uint8_t head[4] = { 0x42, 0x5A, 0x68, (uint8_t)('0' + level) };
-    CK(ctx, cudaMemcpyAsync(d.out.p, head, 4, cudaMemcpyHostToDevice, d.stream));
-    CK(ctx, cudaMemcpyAsync(d.out.as<uint8_t>() + (total_bits >> 3), tail, nbytes - (total_bits >> 3),
-                            cudaMemcpyHostToDevice, d.stream));
-    CK(ctx, cudaMemcpyAsync(d_out, d.out.p, nbytes, cudaMemcpyDeviceToDevice, d.stream));
+    uint8_t *dst = static_cast<uint8_t *>(d_out);
+    CK(ctx, cudaMemcpyAsync(dst, head, 4, cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemcpyAsync(dst + 4, d.out.p, last - 4, cudaMemcpyDeviceToDevice, d.stream));
+    CK(ctx, cudaMemcpyAsync(dst + last, tail, nbytes - last, cudaMemcpyHostToDevice, d.stream));
     CK(ctx, cudaEventRecord(d.ev[7], d.stream));
     CK(ctx, cudaStreamSynchronize(d.stream));
-    finish_stats(ctx, d, false);
+    finish_stats(ctx, shards, false);
     ctx->stats.out_bytes = nbytes;
     *out_len = nbytes;
     return BNZ_OK;

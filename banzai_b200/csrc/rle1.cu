@@ -208,12 +208,14 @@ __global__ void __launch_bounds__(ST) rle_scan_kernel(const u64 *__restrict__ la
 // ------------------------------------------------------------------ kernel 3: emission
 __device__ __forceinline__ u64 g_of(u64 t) { return 5ull * (t / 255ull) + f_of((u32)(t % 255ull)); }
 
-__global__ void __launch_bounds__(WPB * 32) rle_emit_kernel(const u8 *__restrict__ in, u64 N, u64 n_chunks,
+__global__ void __launch_bounds__(WPB * 32) rle_emit_kernel(const u8 *__restrict__ in, u64 N, u64 c_begin, u64 n_chunks,
                                                            const u64 *__restrict__ o_in, const u64 *__restrict__ P,
                                                            const RleBlock *__restrict__ blocks, u32 n_blocks,
                                                            u8 *__restrict__ out)
 {
-    const u64 c = (u64)blockIdx.x * WPB + warp_id();
+    // chunks [c_begin, n_chunks) of the GLOBAL input; `in`, `o_in`, `P` are indexed globally (the
+    // host passes rebased pointers when only a sub-range is resident on this device)
+    const u64 c = c_begin + (u64)blockIdx.x * WPB + warp_id();
     if (c >= n_chunks) return;
     const u32 lane = lane_id();
     const u64 xc = c * CH;
@@ -264,6 +266,11 @@ __global__ void __launch_bounds__(WPB * 32) rle_emit_kernel(const u8 *__restrict
         if ((u32)j >= lb.valid) break;
         if (hm & (1u << j)) r = 0;
         while (i >= bk.c && k + 1 < n_blocks) { k++; bk = blocks[k]; }
+        if (i < bk.s || i >= bk.c) {        // byte belongs to a block owned by another device
+            Pi += need_of(r);
+            r = (r == 254) ? 0 : r + 1;
+            continue;
+        }
         const u32 b = lb.at(j);
         const u32 nb = (j + 1 < 32) ? (((u32)(j + 1) < lb.valid) ? lb.at(j + 1) : NOBYTE) : lb.next;
         u32 rb;            // offset inside the block-relative token
@@ -328,14 +335,14 @@ __device__ __forceinline__ u32 warp_xpow8(u64 e)
     return v;      // same value in every lane
 }
 
-__global__ void __launch_bounds__(WPB * 32) crc_chunk_kernel(const u8 *__restrict__ in, u64 N, u64 n_chunks,
+__global__ void __launch_bounds__(WPB * 32) crc_chunk_kernel(const u8 *__restrict__ in, u64 N, u64 c_begin, u64 n_chunks,
                                                             const RleBlock *__restrict__ blocks, u32 n_blocks,
                                                             u32 *__restrict__ acc)
 {
     __shared__ u32 tab[256];
     for (int i = threadIdx.x; i < 256; i += WPB * 32) tab[i] = c_crc.byte_tab[i];
     __syncthreads();
-    const u64 c = (u64)blockIdx.x * WPB + warp_id();
+    const u64 c = c_begin + (u64)blockIdx.x * WPB + warp_id();
     if (c >= n_chunks) return;
     const u32 lane = lane_id();
     const u64 xc = c * CH;
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(WPB * 32) crc_chunk_kernel(const u8 *__restric
     u32 k = lo;
     RleBlock bk = blocks[k];
 
-    if (xe - xc == CH && xe <= bk.c) {
+    if (xe - xc == CH && xe <= bk.c && xc >= bk.s) {
         // fast path: full chunk inside one block
         const uint4 *p = reinterpret_cast<const uint4 *>(in + xc) + lane * 2;
         uint4 a = __ldg(p), b = __ldg(p + 1);
@@ -366,9 +373,10 @@ __global__ void __launch_bounds__(WPB * 32) crc_chunk_kernel(const u8 *__restric
         if (lane == 0) atomicXor(&acc[k], gf_mul(crc, sh));
     } else {
         // slow path: chunk cut by a block boundary or by the end of the input
-        u64 i = xc;
+        u64 i = max(xc, bk.s);               // bytes before the first local block belong elsewhere
         while (i < xe) {
             while (i >= bk.c && k + 1 < n_blocks) { k++; bk = blocks[k]; }
+            if (i >= bk.c) break;            // past the last local block
             u64 stop = min(xe, bk.c);
             u32 crc = 0;
             if (lane == 0) {
@@ -435,13 +443,14 @@ cudaError_t rle_summary_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunk
     return cudaGetLastError();
 }
 
-cudaError_t rle_emit_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks, const uint64_t *d_oin,
-                            const uint64_t *d_P, const RleBlock *d_blocks, uint32_t n_blocks, uint8_t *d_out,
-                            uint32_t *d_crc_acc, cudaStream_t st)
+cudaError_t rle_emit_launch(const uint8_t *d_in, uint64_t N, uint64_t c_begin, uint64_t c_end,
+                            const uint64_t *d_oin, const uint64_t *d_P, const RleBlock *d_blocks,
+                            uint32_t n_blocks, uint8_t *d_out, uint32_t *d_crc_acc, cudaStream_t st)
 {
-    unsigned grid = (unsigned)((n_chunks + rle::WPB - 1) / rle::WPB);
-    rle::rle_emit_kernel<<<grid, rle::WPB * 32, 0, st>>>(d_in, N, n_chunks, d_oin, d_P, d_blocks, n_blocks, d_out);
-    rle::crc_chunk_kernel<<<grid, rle::WPB * 32, 0, st>>>(d_in, N, n_chunks, d_blocks, n_blocks, d_crc_acc);
+    if (c_end <= c_begin) return cudaSuccess;
+    unsigned grid = (unsigned)((c_end - c_begin + rle::WPB - 1) / rle::WPB);
+    rle::rle_emit_kernel<<<grid, rle::WPB * 32, 0, st>>>(d_in, N, c_begin, c_end, d_oin, d_P, d_blocks, n_blocks, d_out);
+    rle::crc_chunk_kernel<<<grid, rle::WPB * 32, 0, st>>>(d_in, N, c_begin, c_end, d_blocks, n_blocks, d_crc_acc);
     return cudaGetLastError();
 }
 
