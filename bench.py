@@ -52,10 +52,8 @@ def parse_args():
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    from banzai_b200 import dist as D
+    return D.env()
 
 
 # ---------------------------------------------------------------------------------- clocks
@@ -189,15 +187,14 @@ def load_traffic(workload):
 def run_b200(args, kind, size, level, seed):
     rank, world, local = dist_env()
     import torch
-    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible; the B200 arm has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import banzai_b200
     from banzai_b200 import _ffi
+    from banzai_b200 import dist as D
+    group = D.Group(backend="nccl", device=torch.device("cuda", local))
     lib = _ffi.lib
 
     ctx = banzai_b200.Context(devices=[local])
@@ -209,7 +206,7 @@ def run_b200(args, kind, size, level, seed):
     if not h_in:
         raise SystemExit("bnz_host_alloc failed")
     h_arr = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_uint8)), shape=(size,))
-    corpus.by_name(kind, size, seed + rank, out=h_arr)
+    corpus.by_name(kind, size, D.object_seed(seed, rank), out=h_arr)
     d_in = lib.bnz_device_alloc(ctx._h, size + 64)
     out_cap = size // 2 + (64 << 20)
     d_out = lib.bnz_device_alloc(ctx._h, out_cap)
@@ -220,15 +217,10 @@ def run_b200(args, kind, size, level, seed):
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            group.barrier()
             torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = group.max_over_ranks
 
     # ---- device-resident arm ("value")
     for _ in range(args.warmup):
@@ -267,7 +259,7 @@ def run_b200(args, kind, size, level, seed):
         step_ms = t_dev / args.steps * 1e3
         launches = sum(s["kernel_launches"] for s in stats) + sum(s["kernel_launches"] for s in e2e_stats)
         line = {
-            "metric": METRIC, "value": round(world * size / (t_dev / args.steps) / 1e6, 1), "unit": UNIT,
+            "metric": METRIC, "value": round(D.aggregate_throughput(size, world, t_dev, args.steps), 1), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -277,7 +269,7 @@ def run_b200(args, kind, size, level, seed):
                        "sharding": "one independent object per GPU, no collective",
                        "compressed_bytes_per_gpu": int(out_len),
                        "bwt_radix_bits": stats[-1]["bwt_radix_bits"]},
-            "e2e": {"value": round(world * size / (t_e2e / args.steps) / 1e6, 1), "unit": UNIT,
+            "e2e": {"value": round(D.aggregate_throughput(size, world, t_e2e, args.steps), 1), "unit": UNIT,
                     "h2d_bytes_per_step": int(e2e_stats[-1]["h2d_bytes"]),
                     "d2h_bytes_per_step": int(e2e_stats[-1]["d2h_bytes"])},
             "gpu_launches": int(launches),
@@ -312,8 +304,7 @@ def run_b200(args, kind, size, level, seed):
     lib.bnz_device_free(ctx._h, d_out)
     lib.bnz_host_free(h_in)
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    group.close()
 
 
 def main():
