@@ -128,7 +128,8 @@ class Context:
             if with_stats:
                 item = item + ({"rounds": st[b].rounds, "tied": st[b].tied,
                                 "sum_active": st[b].sum_active,
-                                "sum_active_passes": st[b].sum_active_passes},)
+                                "sum_active_passes": st[b].sum_active_passes,
+                                "cycles": st[b].cycles, "score": st[b].pad},)
             res.append(item)
         return res
 

@@ -525,8 +525,9 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) bwt_cluster_kernel(BwtA
         if (c == 0 && tid < 8) (&ctl->totals[0][0])[tid] = 0;
         for (int i = tid; i < 256; i += T) sm.present[i] = 0;
         cluster.sync();
-        const u32 blk = __ldcg(&ctl->blk);
-        if (blk >= a.n_blocks) break;
+        const u32 qpos = __ldcg(&ctl->blk);
+        if (qpos >= a.n_blocks) break;
+        const u32 blk = a.order ? a.order[qpos] : qpos;
 
         const u8 *S = a.rle + a.blk_off[blk];
         u8 *bwt_out = a.bwt + a.blk_off[blk];

@@ -487,9 +487,10 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
     for (;;) {
         if (tid == 0) sm.s_block = atomicAdd(a.next_block, 1u);
         __syncthreads();
-        const u32 blk = sm.s_block;
+        const u32 qpos = sm.s_block;
         __syncthreads();
-        if (blk >= a.n_blocks) break;
+        if (qpos >= a.n_blocks) break;
+        const u32 blk = a.order ? a.order[qpos] : qpos;
 
         const u8 *S = a.rle + a.blk_off[blk];
         u8 *bwt_out = a.bwt + a.blk_off[blk];
@@ -568,7 +569,71 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// cost predictor: blocks with many long repeats need many doubling rounds.  Windows are sampled
+// by CONTENT (a 4-byte hash decides), so both copies of a repeat are sampled, and a Bloom filter
+// in shared memory tells whether the 24-byte window was seen before.
+// ---------------------------------------------------------------------------------------
+constexpr int PT = 512;
+constexpr u32 BLOOM_BITS = 1u << 19;                 // 64 KB
+__global__ void __launch_bounds__(PT) bwt_predict_kernel(const u8 *__restrict__ rle, const u64 *__restrict__ blk_off,
+                                                        const u32 *__restrict__ blk_len, u32 *__restrict__ score)
+{
+    extern __shared__ u32 bloom[];
+    __shared__ u32 scratch[40];
+    const u32 b = blockIdx.x, tid = threadIdx.x;
+    const u8 *S = rle + blk_off[b];
+    const u32 n = blk_len[b];
+    for (u32 i = tid; i < BLOOM_BITS / 32; i += PT) bloom[i] = 0;
+    __syncthreads();
+    u32 hits = 0;
+    // lanes take consecutive positions (coalesced); 4 positions per thread and iteration
+    for (u32 base = 0; base + 24 <= n; base += PT * 4) {
+        const u32 i0 = base + tid * 4;
+        if (i0 + 28 > n) continue;
+        // 8 bytes starting at i0 cover the four 4-byte windows i0..i0+3
+        u32 lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            lo |= (u32)S[i0 + j] << (8 * j);
+            hi |= (u32)S[i0 + 4 + j] << (8 * j);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const u32 w0 = q ? __funnelshift_r(lo, hi, 8 * q) : lo;
+            if (((w0 * 2654435761u) >> 28) != 0) continue;      // content-defined 1/16 sampling
+            const u32 i = i0 + q;
+            u32 h1 = 2166136261u, h2 = 0x9747b28cu;
+#pragma unroll
+            for (int j = 0; j < 24; j++) {
+                u32 c = S[i + j];
+                h1 = (h1 ^ c) * 16777619u;
+                h2 = (h2 + c) * 0xcc9e2d51u;
+                h2 = (h2 << 13) | (h2 >> 19);
+            }
+            h1 &= BLOOM_BITS - 1;
+            h2 &= BLOOM_BITS - 1;
+            u32 o1 = atomicOr(&bloom[h1 >> 5], 1u << (h1 & 31));
+            u32 o2 = atomicOr(&bloom[h2 >> 5], 1u << (h2 & 31));
+            if (((o1 >> (h1 & 31)) & 1u) && ((o2 >> (h2 & 31)) & 1u)) hits++;
+        }
+    }
+    u32 tot = block_sum<PT>(hits, scratch);
+    if (tid == 0) score[b] = tot;
+}
+
 }  // namespace bwt
+
+cudaError_t bwt_predict_launch(const uint8_t *d_rle, const uint64_t *d_blk_off, const uint32_t *d_blk_len,
+                               uint32_t n_blocks, uint32_t *d_score, cudaStream_t stream)
+{
+    if (n_blocks == 0) return cudaSuccess;
+    size_t smem = bwt::BLOOM_BITS / 8;
+    cudaError_t e = cudaFuncSetAttribute(bwt::bwt_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bwt::bwt_predict_kernel<<<n_blocks, bwt::PT, smem, stream>>>(d_rle, d_blk_off, d_blk_len, d_score);
+    return cudaGetLastError();
+}
 
 size_t bwt_smem_bytes(int bits)
 {

@@ -65,7 +65,13 @@ struct BwtArgs {
     uint32_t *ws_rank;            // per CTA: ws_stride ranks
     size_t ws_stride;             // >= max block length (+ cluster slack), multiple of 16
     void *ws_ctl;                 // cluster kernel only: per cluster BWT_CTL_BYTES of control state
+    const uint32_t *order;        // optional: queue position -> block id (longest-first schedule)
 };
+
+// cheap per-block cost predictor for the work queue: counts content-sampled 24-byte windows that
+// were seen before inside the block (Bloom filter in shared memory)
+cudaError_t bwt_predict_launch(const uint8_t *d_rle, const uint64_t *d_blk_off, const uint32_t *d_blk_len,
+                               uint32_t n_blocks, uint32_t *d_score, cudaStream_t stream);
 
 size_t bwt_smem_bytes(int bits);
 int bwt_passes(int bits);

@@ -5,6 +5,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <thread>
 #include <vector>
@@ -72,7 +73,7 @@ struct Device {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     // arenas (grown on demand, kept across calls)
-    DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl;
+    DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, bwt_score, bwt_order;
     DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, rle_blocks, crc_acc;
     DevBuf seg_base, seg_list, seg_cnt, seg_state, num_names, syms, sym_off, sym_len, freqs;
     DevBuf lens, codes, tf, num_tables, num_sel, span_base, hdr, hdr_bits, crc, blk_bits, blk_bitoff,
@@ -91,6 +92,8 @@ struct bnz_ctx {
     int ctas_per_sm = 0;
     int bwt_cluster = -1;         // CTAs per bzip2 block (-1: auto, 0/1: single-CTA kernel)
     int bwt_threads = 512;
+    int bwt_lpt = 0;                   // longest-predicted-first work queue (measured: no robust gain, off)
+    std::vector<uint32_t> last_scores; // predictor output of the last sort (debug / tests)
     int bwt_cluster_below = 400;       // auto mode: cluster kernel when a device gets fewer blocks than this
     // cached pinned output buffer handed to the caller by bnz_encode / returned by bnz_free
     uint8_t *out_cache = nullptr;
@@ -190,7 +193,7 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
         cudaSetDevice(d.id);
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (DevBuf *b : { &d.in, &d.rle, &d.bwt, &d.blk_off, &d.blk_len, &d.ptr, &d.has_byte,
-                           &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.ch_lasthead, &d.ch_meta,
+                           &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.bwt_score, &d.bwt_order, &d.ch_lasthead, &d.ch_meta,
                            &d.ch_restsum, &d.ch_oin, &d.ch_P, &d.rle_blocks, &d.crc_acc, &d.seg_base,
                            &d.seg_list, &d.seg_cnt, &d.seg_state, &d.num_names, &d.syms, &d.sym_off,
                            &d.sym_len, &d.freqs, &d.lens, &d.codes, &d.tf, &d.num_tables, &d.num_sel,
@@ -219,6 +222,10 @@ extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
     if (!strcmp(key, "bwt_cluster")) {
         if (value < -1 || value > BWT_CLUSTER_MAX) return BNZ_EINVAL;
         ctx->bwt_cluster = (int)value;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "bwt_lpt")) {
+        ctx->bwt_lpt = value != 0;
         return BNZ_OK;
     }
     if (!strcmp(key, "bwt_cluster_below")) {
@@ -317,6 +324,7 @@ static int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t
     a.next_block = d.counters.as<uint32_t>();
     a.n_blocks = n_blocks;
     a.ws_ctl = nullptr;
+    a.order = nullptr;
 
     // auto: many blocks -> one persistent CTA per block (best aggregate throughput);
     // few blocks -> one cluster per block so that every SM has work and the randomly accessed
@@ -348,6 +356,23 @@ static int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t
     if (per_sm <= 0) return fail(ctx, BNZ_ECUDA, "bwt kernel does not fit on an SM");
     if (ctx->ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->ctas_per_sm);
     int grid = (int)std::min<uint64_t>((uint64_t)n_blocks, (uint64_t)d.sm_count * per_sm);
+    if (ctx->bwt_lpt && n_blocks > (uint32_t)grid) {
+        // blocks differ several-fold in sort cost (doubling rounds); with a plain index-order queue
+        // the last wave's long blocks leave most SMs idle.  Predict, then schedule longest first.
+        CK(ctx, d.bwt_score.ensure((size_t)n_blocks * 4));
+        CK(ctx, d.bwt_order.ensure((size_t)n_blocks * 4));
+        CK(ctx, bwt_predict_launch(d_rle, d_blk_off, d_blk_len, n_blocks, d.bwt_score.as<uint32_t>(), d.stream));
+        d.launches++;
+        std::vector<uint32_t> score(n_blocks), order(n_blocks);
+        CK(ctx, cudaMemcpyAsync(score.data(), d.bwt_score.p, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, d.stream));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+        ctx->last_scores = score;
+        for (uint32_t i = 0; i < n_blocks; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return score[x] > score[y]; });
+        CK(ctx, cudaMemcpyAsync(d.bwt_order.p, order.data(), (size_t)n_blocks * 4, cudaMemcpyHostToDevice, d.stream));
+        CK(ctx, cudaStreamSynchronize(d.stream));      // `order` is a stack vector
+        a.order = d.bwt_order.as<uint32_t>();
+    }
     size_t stride = ((size_t)max_len + 15) & ~(size_t)15;
     CK(ctx, d.ws_rec.ensure((size_t)grid * 2 * stride * sizeof(uint64_t)));
     CK(ctx, d.ws_rank.ensure((size_t)grid * stride * sizeof(uint32_t)));
@@ -427,9 +452,10 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
             stats_out[b].n = st[b].n;
             stats_out[b].rounds = st[b].rounds;
             stats_out[b].tied = st[b].tied;
-            stats_out[b].pad = 0;
+            stats_out[b].pad = b < ctx->last_scores.size() ? ctx->last_scores[b] : 0;
             stats_out[b].sum_active = st[b].sum_active;
             stats_out[b].sum_active_passes = st[b].sum_active_passes;
+            stats_out[b].cycles = st[b].cyc_build + st[b].cyc_radix + st[b].cyc_rerank;
         }
     }
     s.bwt_algorithmic_bytes = 9 * s.bwt_n + 16 * s.bwt_sum_active_passes + 36 * s.bwt_sum_active;
@@ -836,6 +862,12 @@ struct Shard {
     uint64_t bit_base = 0;             // global bit offset of the shard's first block
     int rc = BNZ_OK;
     std::string err;
+    // lanes on one GPU: the persistent BWT kernels must not share the SMs, so lane g's sort waits
+    // for lane g-1's (event recorded on that lane's stream; the flag orders the host threads)
+    Shard *bwt_after = nullptr;
+    std::atomic<int> bwt_recorded{0};
+    Shard() = default;
+    Shard(const Shard &o) { d = o.d; }
 };
 
 // K1 emit .. K7 + headers for one shard; ends with a host sync that yields block_bits.
@@ -867,11 +899,20 @@ static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t
     CK(ctx, d.ptr.ensure((size_t)nb * 4));
     CK(ctx, d.has_byte.ensure((size_t)nb * 256));
     CK(ctx, d.bwt_stats.ensure((size_t)nb * sizeof(BwtStats)));
+    if (sh.bwt_after) {
+        while (sh.bwt_after->bwt_recorded.load(std::memory_order_acquire) == 0) std::this_thread::yield();
+        if (sh.bwt_after->bwt_recorded.load() > 0) CK(ctx, cudaStreamWaitEvent(d.stream, sh.bwt_after->d->ev[3], 0));
+        CK(ctx, cudaEventRecord(d.ev[2], d.stream));       // RLE stage ends where the sort may start
+    }
     rc = run_bwt_device(ctx, d, d.rle.as<uint8_t>(), d.bwt.as<uint8_t>(), d.blk_off.as<uint64_t>(),
                         d.blk_len.as<uint32_t>(), nb, bt.max_len, d.ptr.as<uint32_t>(), d.has_byte.as<uint8_t>(),
                         d.bwt_stats.as<BwtStats>());
-    if (rc != BNZ_OK) return rc;
+    if (rc != BNZ_OK) {
+        sh.bwt_recorded.store(-1, std::memory_order_release);
+        return rc;
+    }
     CK(ctx, cudaEventRecord(d.ev[3], d.stream));
+    sh.bwt_recorded.store(1, std::memory_order_release);
 
     // K5 (the RLE1 images are dead now: their buffer holds the MTF index bytes)
     rc = run_mtf_device(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>());
@@ -1005,12 +1046,14 @@ static int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, s
     int rc = rle_plan(ctx, d0, d_in, h_in, N, level, blocks);
     if (rc != BNZ_OK) return rc;
 
+    CK(ctx, cudaEventRecord(d0.ev[8], d0.stream));       // input + chunk tables resident on device 0
     const size_t n_dev = std::min(ctx->devs.size(), std::max<size_t>(1, blocks.size()));
     std::vector<uint32_t> cut = split_blocks(blocks, n_dev);
-    shards.assign(n_dev, Shard());
+    shards = std::vector<Shard>(n_dev);
     for (size_t g = 0; g < n_dev; g++) {
         Shard &sh = shards[g];
         sh.d = &ctx->devs[g];
+        if (g > 0 && ctx->devs[g].id == ctx->devs[g - 1].id) sh.bwt_after = &shards[g - 1];
         sh.blocks.assign(blocks.begin() + cut[g], blocks.begin() + cut[g + 1]);
         const uint64_t off0 = sh.blocks.empty() ? 0 : sh.blocks.front().rle_off;
         for (RleBlock &b : sh.blocks) b.rle_off -= off0;
@@ -1020,9 +1063,21 @@ static int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, s
     auto work = [&](size_t g) -> int {
         Shard &sh = shards[g];
         Device &d = *sh.d;
-        if (sh.blocks.empty()) return BNZ_OK;
+        if (sh.blocks.empty()) {
+            sh.bwt_recorded.store(-1, std::memory_order_release);
+            return BNZ_OK;
+        }
         CK(ctx, cudaSetDevice(d.id));
-        if (g == 0) return shard_model(ctx, sh, d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
+        if (d.id == d0.id) {
+            // same physical GPU (lane 0, or an extra lane that overlaps its stages with the other
+            // lanes' kernels): the input and the chunk tables are already resident
+            if (g != 0) {
+                CK(ctx, cudaStreamWaitEvent(d.stream, d0.ev[8], 0));
+                CK(ctx, cudaEventRecord(d.ev[0], d.stream));
+                CK(ctx, cudaEventRecord(d.ev[1], d.stream));
+            }
+            return shard_model(ctx, sh, d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
+        }
         // other devices: make their input range and chunk tables resident
         CK(ctx, cudaEventRecord(d.ev[0], d.stream));
         const uint64_t c0 = sh.blocks.front().s / RLE_CHUNK;
@@ -1048,6 +1103,7 @@ static int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, s
             th.emplace_back([&, g]() {
                 t_err_sink = &shards[g].err;
                 shards[g].rc = work(g);
+                if (shards[g].bwt_recorded.load() == 0) shards[g].bwt_recorded.store(-1, std::memory_order_release);
                 t_err_sink = nullptr;
             });
         for (std::thread &t : th) t.join();
@@ -1163,7 +1219,8 @@ extern "C" int bnz_encode_device(bnz_ctx *ctx, const void *d_in, const uint8_t *
     *out_len = 0;
     if (level < 1 || level > 9) return fail(ctx, BNZ_EINVAL, "level must be in 1..=9 (lib/lib.rs:89)");
     if (in_len == 0 || !d_in || !h_in) return BNZ_EINVAL;
-    if (ctx->devs.size() != 1) return fail(ctx, BNZ_EINVAL, "bnz_encode_device needs a single-device context");
+    for (Device &dv : ctx->devs)
+        if (dv.id != ctx->devs[0].id) return fail(ctx, BNZ_EINVAL, "bnz_encode_device needs a single-GPU context");
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.in_bytes = in_len;
     Device &d = ctx->devs[0];
@@ -1172,28 +1229,60 @@ extern "C" int bnz_encode_device(bnz_ctx *ctx, const void *d_in, const uint8_t *
     std::vector<Shard> shards;
     int rc = encode_all(ctx, h_in, (const uint8_t *)d_in, in_len, level, shards, crcs, &total_bits);
     if (rc != BNZ_OK) return rc;
-    size_t bytes = 0;
-    rc = shard_pack(ctx, shards[0], &bytes);
-    if (rc != BNZ_OK) return rc;
     const size_t nbytes = (size_t)((total_bits + 80 + 7) / 8);
-    if (nbytes > d_out_cap) return fail(ctx, BNZ_EINVAL, "d_out_cap too small");
-    // assemble the stream in d_out: 4 header bytes, the packed blocks (d.out word 0 is global
-    // word 1 because shard 0 starts at bit 32), then the footer patched over the last partial byte
+    if (nbytes + 8 > d_out_cap) return fail(ctx, BNZ_EINVAL, "d_out_cap too small");
+    uint8_t *dst = static_cast<uint8_t *>(d_out);
+
+    // every lane packs at its bit phase and copies device-to-device; a word shared by two lanes
+    // is merged through the host (4 bytes)
+    std::vector<uint32_t> first_word(shards.size(), 0);
+    for (size_t g = 0; g < shards.size(); g++) {
+        Shard &sh = shards[g];
+        if (sh.blocks.empty()) continue;
+        Device &dl = *sh.d;
+        size_t bytes = 0;
+        rc = shard_pack(ctx, sh, &bytes);
+        if (rc != BNZ_OK) return rc;
+        const size_t w0 = (size_t)(sh.bit_base >> 5) * 4;
+        if (g == 0) {
+            CK(ctx, cudaMemcpyAsync(dst + w0, dl.out.p, bytes, cudaMemcpyDeviceToDevice, dl.stream));
+        } else {
+            CK(ctx, cudaMemcpyAsync(&first_word[g], dl.out.p, 4, cudaMemcpyDeviceToHost, dl.stream));
+            if (bytes > 4)
+                CK(ctx, cudaMemcpyAsync(dst + w0 + 4, dl.out.as<uint8_t>() + 4, bytes - 4, cudaMemcpyDeviceToDevice, dl.stream));
+        }
+    }
+    for (Shard &sh : shards)
+        if (!sh.blocks.empty()) CK(ctx, cudaStreamSynchronize(sh.d->stream));
+    for (size_t g = 1; g < shards.size(); g++) {
+        if (shards[g].blocks.empty()) continue;
+        uint8_t *w = dst + (size_t)(shards[g].bit_base >> 5) * 4;
+        uint32_t cur = 0;
+        if (shards[g].bit_base & 31) {
+            CK(ctx, cudaMemcpyAsync(&cur, w, 4, cudaMemcpyDeviceToHost, d.stream));
+            CK(ctx, cudaStreamSynchronize(d.stream));
+        }
+        cur |= first_word[g];
+        CK(ctx, cudaMemcpyAsync(w, &cur, 4, cudaMemcpyHostToDevice, d.stream));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+    }
+    // header, and the footer patched over the last partial byte
     uint8_t tail[16] = { 0 };
     const uint64_t tb = total_bits & 7;
-    const size_t last = (size_t)(total_bits >> 3);          // global byte index of the partial byte
+    const size_t last = (size_t)(total_bits >> 3);
     uint8_t lastbyte = 0;
-    if (tb) CK(ctx, cudaMemcpyAsync(&lastbyte, d.out.as<uint8_t>() + (last - 4), 1, cudaMemcpyDeviceToHost, d.stream));
-    CK(ctx, cudaStreamSynchronize(d.stream));
+    if (tb) {
+        CK(ctx, cudaMemcpyAsync(&lastbyte, dst + last, 1, cudaMemcpyDeviceToHost, d.stream));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+    }
     tail[0] = lastbyte;
     put_bits_host(tail, tb, 0x177245385090ull, 48);
     put_bits_host(tail, tb + 48, fold_stream_crc(crcs), 32);
     const uint8_t head[4] = { 0x42, 0x5A, 0x68, (uint8_t)('0' + level) };
-    uint8_t *dst = static_cast<uint8_t *>(d_out);
     CK(ctx, cudaMemcpyAsync(dst, head, 4, cudaMemcpyHostToDevice, d.stream));
-    CK(ctx, cudaMemcpyAsync(dst + 4, d.out.p, last - 4, cudaMemcpyDeviceToDevice, d.stream));
     CK(ctx, cudaMemcpyAsync(dst + last, tail, nbytes - last, cudaMemcpyHostToDevice, d.stream));
-    CK(ctx, cudaEventRecord(d.ev[7], d.stream));
+    for (Shard &sh : shards)
+        if (!sh.blocks.empty()) CK(ctx, cudaEventRecord(sh.d->ev[7], sh.d->stream));
     CK(ctx, cudaStreamSynchronize(d.stream));
     finish_stats(ctx, shards, false);
     ctx->stats.out_bytes = nbytes;

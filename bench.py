@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--workload", default="mixed-1GiB-L9", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--radix-bits", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=1, help="concurrent block batches per GPU")
     return ap.parse_args()
 
 
@@ -197,7 +198,7 @@ def run_b200(args, kind, size, level, seed):
     group = D.Group(backend="nccl", device=torch.device("cuda", local))
     lib = _ffi.lib
 
-    ctx = banzai_b200.Context(devices=[local])
+    ctx = banzai_b200.Context(devices=[local] * args.lanes)
     if args.radix_bits:
         ctx.set("bwt_radix_bits", args.radix_bits)
 

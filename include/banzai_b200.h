@@ -136,6 +136,7 @@ BNZ_API int bnz_stage_rle1(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int l
 typedef struct bnz_bwt_block_stats {
     uint32_t n, rounds, tied, pad;
     uint64_t sum_active, sum_active_passes;
+    uint64_t cycles;              /* SM cycles the block occupied its CTA / cluster */
 } bnz_bwt_block_stats;
 BNZ_API int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t *blk_off,
                           const uint32_t *blk_len, size_t n_blocks, int level, uint8_t *bwt_out,

@@ -116,3 +116,29 @@ def test_size_independent_properties_at_scale(ctx):
     assert bz2.decompress(out1) == data.tobytes()
     out2 = ctx.encode_bytes(data, 9)
     assert out1 == out2
+
+
+def test_lanes_on_one_gpu_and_device_resident_entry():
+    """several concurrent block batches ("lanes") on the same GPU, and bnz_encode_device, give the
+    same bytes as the plain call"""
+    import ctypes as C
+
+    import banzai_b200
+    from banzai_b200 import _ffi
+    data = corpus.mixed(9 * 1000 * 1000)
+    want = O.encode(data, 9)
+    for lanes in (1, 2, 3):
+        with banzai_b200.Context(devices=[0] * lanes) as c:
+            assert c.encode_bytes(data, 9) == want
+            lib = _ffi.lib
+            n = data.size
+            d_in = lib.bnz_device_alloc(c._h, n + 64)
+            cap = n + (1 << 20)
+            d_out = lib.bnz_device_alloc(c._h, cap)
+            c._check(lib.bnz_memcpy_h2d(c._h, d_in, data.ctypes.data_as(C.c_void_p), n))
+            olen = c.encode_device(d_in, data.ctypes.data_as(C.c_void_p), n, 9, d_out, cap)
+            back = np.zeros(olen, np.uint8)
+            c._check(lib.bnz_memcpy_d2h(c._h, back.ctypes.data_as(C.c_void_p), d_out, olen))
+            assert back.tobytes() == want
+            lib.bnz_device_free(c._h, d_in)
+            lib.bnz_device_free(c._h, d_out)
