@@ -35,7 +35,9 @@ cudaError_t rle_summary_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunk
                                cudaStream_t st);
 cudaError_t rle_emit_launch(const uint8_t *d_in, uint64_t N, uint64_t c_begin, uint64_t c_end,
                             const uint64_t *d_oin, const uint64_t *d_P, const RleBlock *d_blocks,
-                            uint32_t n_blocks, uint8_t *d_out, uint32_t *d_crc_acc, cudaStream_t st);
+                            uint32_t n_blocks, uint8_t *d_out, cudaStream_t st);
+cudaError_t crc_launch(const uint8_t *d_in, uint64_t N, uint64_t c_begin, uint64_t c_end, const RleBlock *d_blocks,
+                       uint32_t n_blocks, uint32_t *d_crc_acc, uint32_t *d_crc, cudaStream_t st);
 int rle_walk_cuts(const uint8_t *in, uint64_t N, int level, const uint64_t *P, const uint64_t *o_in,
                   uint64_t n_chunks, std::vector<RleBlock> &blocks);
 

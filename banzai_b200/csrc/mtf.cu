@@ -187,6 +187,11 @@ __global__ void __launch_bounds__(NT1) mtf_apply_kernel(MtfArgs a)
         u32 o4[4] = { 0, 0, 0, 0 };
 #pragma unroll
         for (int j = 0; j < 16; j++) {
+            // a whole word equal to the current front byte is four zero indices: nothing moves
+            if ((j & 3) == 0 && p + j + 4 <= end && w4[j >> 2] == (u32)(hq & 0xff) * 0x01010101u) {
+                j += 3;
+                continue;
+            }
             if (p + j < end) {
                 const u64 c = (w4[j >> 2] >> ((j & 3) * 8)) & 0xffu;
                 const u64 x = hq ^ (c * ONES);

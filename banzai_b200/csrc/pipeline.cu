@@ -72,6 +72,7 @@ struct Device {
     int id = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;     // side stream: block CRCs run beside the sort
     // arenas (grown on demand, kept across calls)
     DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, bwt_score, bwt_order;
     DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, rle_blocks, crc_acc;
@@ -155,7 +156,8 @@ extern "C" int bnz_ctx_create_on(bnz_ctx **out, const int *device_ids, int n_dev
         d.id = device_ids[i];
         cudaDeviceProp prop;
         if (cudaSetDevice(d.id) != cudaSuccess || cudaGetDeviceProperties(&prop, d.id) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking) != cudaSuccess) {
             delete ctx;
             return BNZ_ECUDA;
         }
@@ -206,6 +208,7 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
         d.h_oin.release();
         d.h_acc.release();
         if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.stream2) cudaStreamDestroy(d.stream2);
     }
     if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
     delete ctx;
@@ -499,10 +502,10 @@ static int rle_plan(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const uint8_t 
 // rle_off rebased to 0; in_base / oin_base / P_base are device pointers indexed by GLOBAL input
 // position / chunk (rebased by the caller when only a sub-range is resident).
 static int rle_emit_shard(bnz_ctx *ctx, Device &d, const uint8_t *in_base, uint64_t N, const uint64_t *oin_base,
-                          const uint64_t *P_base, const std::vector<RleBlock> &blocks, std::vector<uint32_t> &crcs,
+                          const uint64_t *P_base, const std::vector<RleBlock> &blocks, std::vector<uint32_t> *crcs,
                           uint64_t *rle_total)
 {
-    crcs.clear();
+    if (crcs) crcs->clear();
     *rle_total = 0;
     const size_t nb = blocks.size();
     if (nb == 0) return BNZ_OK;
@@ -516,17 +519,26 @@ static int rle_emit_shard(bnz_ctx *ctx, Device &d, const uint8_t *in_base, uint6
     const uint64_t c_end = (blocks.back().c + RLE_CHUNK - 1) / RLE_CHUNK;
     CK(ctx, d.rle_blocks.ensure(nb * sizeof(RleBlock)));
     CK(ctx, d.crc_acc.ensure(nb * 4));
+    CK(ctx, d.crc.ensure(nb * 4));
     CK(ctx, d.rle.ensure(total));
     CK(ctx, cudaMemcpyAsync(d.rle_blocks.p, blocks.data(), nb * sizeof(RleBlock), cudaMemcpyHostToDevice, d.stream));
     CK(ctx, cudaMemsetAsync(d.crc_acc.p, 0, nb * 4, d.stream));
+    CK(ctx, cudaEventRecord(d.ev[9], d.stream));
     CK(ctx, rle_emit_launch(in_base, N, c_begin, c_end, oin_base, P_base, d.rle_blocks.as<RleBlock>(), (uint32_t)nb,
-                            d.rle.as<uint8_t>(), d.crc_acc.as<uint32_t>(), d.stream));
-    d.launches += 2;
-    CK(ctx, d.h_acc.ensure(nb * 4));
-    CK(ctx, cudaMemcpyAsync(d.h_acc.p, d.crc_acc.p, nb * 4, cudaMemcpyDeviceToHost, d.stream));
-    CK(ctx, cudaStreamSynchronize(d.stream));
-    crcs.resize(nb);
-    for (size_t b = 0; b < nb; b++) crcs[b] = crc_finalize(d.h_acc.as<uint32_t>()[b], blocks[b].c - blocks[b].s);
+                            d.rle.as<uint8_t>(), d.stream));
+    // K2 on the side stream; d.ev[10] marks d.crc complete
+    CK(ctx, cudaStreamWaitEvent(d.stream2, d.ev[9], 0));
+    CK(ctx, crc_launch(in_base, N, c_begin, c_end, d.rle_blocks.as<RleBlock>(), (uint32_t)nb, d.crc_acc.as<uint32_t>(),
+                       d.crc.as<uint32_t>(), d.stream2));
+    CK(ctx, cudaEventRecord(d.ev[10], d.stream2));
+    d.launches += 3;
+    if (crcs) {
+        CK(ctx, d.h_acc.ensure(nb * 4));
+        CK(ctx, cudaStreamWaitEvent(d.stream, d.ev[10], 0));
+        CK(ctx, cudaMemcpyAsync(d.h_acc.p, d.crc.p, nb * 4, cudaMemcpyDeviceToHost, d.stream));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+        crcs->assign(d.h_acc.as<uint32_t>(), d.h_acc.as<uint32_t>() + nb);
+    }
     return BNZ_OK;
 }
 
@@ -538,7 +550,7 @@ static int run_rle_device(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const ui
     *rle_total = 0;
     int rc = rle_plan(ctx, d, d_in, h_in, N, level, blocks);
     if (rc != BNZ_OK || blocks.empty()) return rc;
-    return rle_emit_shard(ctx, d, d_in, N, d.ch_oin.as<uint64_t>(), d.ch_P.as<uint64_t>(), blocks, crcs, rle_total);
+    return rle_emit_shard(ctx, d, d_in, N, d.ch_oin.as<uint64_t>(), d.ch_P.as<uint64_t>(), blocks, &crcs, rle_total);
 }
 
 extern "C" int bnz_stage_rle1(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int level, uint64_t *blk_in_off,
@@ -877,7 +889,7 @@ static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t
 {
     Device &d = *sh.d;
     uint64_t rle_total = 0;
-    int rc = rle_emit_shard(ctx, d, in_base, N, oin_base, P_base, sh.blocks, sh.crcs, &rle_total);
+    int rc = rle_emit_shard(ctx, d, in_base, N, oin_base, P_base, sh.blocks, nullptr, &rle_total);
     if (rc != BNZ_OK) return rc;
     CK(ctx, cudaEventRecord(d.ev[2], d.stream));
     const uint32_t nb = (uint32_t)sh.blocks.size();
@@ -892,7 +904,6 @@ static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t
     bt.build();
     rc = upload_batch(ctx, d, bt);
     if (rc != BNZ_OK) return rc;
-    CK(ctx, upload(d.crc, sh.crcs, d.stream));
 
     // K3/K4
     CK(ctx, d.bwt.ensure(rle_total));
@@ -919,10 +930,13 @@ static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t
     if (rc != BNZ_OK) return rc;
     CK(ctx, cudaEventRecord(d.ev[4], d.stream));
 
-    // K6/K7 + headers + block bit lengths
+    // K6/K7 + headers + block bit lengths (the headers need the block CRCs from the side stream)
+    CK(ctx, cudaStreamWaitEvent(d.stream, d.ev[10], 0));
     rc = run_huff_model_device(ctx, d, bt, level, 1, 0, 0, sh.ha);
     if (rc != BNZ_OK) return rc;
     sh.bst.resize(nb);
+    sh.crcs.resize(nb);
+    CK(ctx, cudaMemcpyAsync(sh.crcs.data(), d.crc.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaMemcpyAsync(&sh.block_bits, d.total_bits.p, 8, cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaMemcpyAsync(sh.bst.data(), d.bwt_stats.p, (size_t)nb * sizeof(BwtStats), cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaEventRecord(d.ev[5], d.stream));

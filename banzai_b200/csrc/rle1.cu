@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(WPB * 32) rle_summary_kernel(const u8 *__restr
 // single CTA: o_in[c] = run offset of the chunk's first byte, P[c] = cost prefix at the chunk
 // start, P[n_chunks] = total.
 constexpr int ST = 1024;
+constexpr int SI = 8;                 // chunks per thread and tile
 __global__ void __launch_bounds__(ST) rle_scan_kernel(const u64 *__restrict__ lasthead, const u32 *__restrict__ meta,
                                                      const u32 *__restrict__ restsum, u64 n_chunks,
                                                      u64 *__restrict__ o_in, u64 *__restrict__ P)
@@ -141,12 +142,21 @@ __global__ void __launch_bounds__(ST) rle_scan_kernel(const u64 *__restrict__ la
     __shared__ u64 sh[40];
     u64 carry_head = 0, carry_sum = 0;
     const u32 lane = lane_id(), w = warp_id();
-    for (u64 base = 0; base < n_chunks; base += ST) {
-        const u64 c = base + threadIdx.x;
-        const bool ok = c < n_chunks;
-        u64 lh = ok ? lasthead[c] : 0;
-        // exclusive max scan
-        u64 inc = lh;
+    for (u64 base = 0; base < n_chunks; base += (u64)ST * SI) {
+        const u64 c0 = base + (u64)threadIdx.x * SI;
+        u64 lh[SI];
+        u32 mt[SI], rs[SI];
+        u64 agg = 0;
+#pragma unroll
+        for (int k = 0; k < SI; k++) {
+            const bool ok = c0 + k < n_chunks;
+            lh[k] = ok ? lasthead[c0 + k] : 0;
+            mt[k] = ok ? meta[c0 + k] : 0;
+            rs[k] = ok ? restsum[c0 + k] : 0;
+            agg = max(agg, lh[k]);
+        }
+        // block-wide exclusive max scan of the per-thread maxima
+        u64 inc = agg;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             u64 t = __shfl_up_sync(0xffffffffu, inc, d);
@@ -157,8 +167,7 @@ __global__ void __launch_bounds__(ST) rle_scan_kernel(const u64 *__restrict__ la
         if (lane == 31) sh[w] = inc;
         __syncthreads();
         if (w == 0) {
-            u64 v = sh[lane];
-            u64 vi = v;
+            u64 vi = sh[lane];
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 u64 t = __shfl_up_sync(0xffffffffu, vi, d);
@@ -171,21 +180,28 @@ __global__ void __launch_bounds__(ST) rle_scan_kernel(const u64 *__restrict__ la
         }
         __syncthreads();
         u64 hprev = max(max(sh[w], ex), carry_head);
-        u64 tile_head = sh[32];
+        const u64 tile_head = sh[32];
         __syncthreads();
 
-        u64 s = 0, oin = 0;
-        if (ok) {
-            u32 m = meta[c];
-            u32 lead = m & 0x7fffffffu;
-            if (m & 0x80000000u) oin = c * CH - (hprev - 1);
-            u32 r_in = (u32)(oin % 255u);
-            u32 t = r_in + lead;
-            s = 5u * (t / 255u) + f_of(t % 255u) - f_of(r_in) + restsum[c];
-            o_in[c] = oin;
+        u64 sv[SI];
+        u64 tsum = 0;
+#pragma unroll
+        for (int k = 0; k < SI; k++) {
+            sv[k] = 0;
+            if (c0 + k < n_chunks) {
+                const u32 lead = mt[k] & 0x7fffffffu;
+                u64 oin = 0;
+                if (mt[k] & 0x80000000u) oin = (c0 + k) * CH - (hprev - 1);
+                const u32 r_in = (u32)(oin % 255u);
+                const u32 t = r_in + lead;
+                sv[k] = 5u * (t / 255u) + f_of(t % 255u) - f_of(r_in) + rs[k];
+                o_in[c0 + k] = oin;
+            }
+            hprev = max(hprev, lh[k]);
+            tsum += sv[k];
         }
-        // exclusive sum scan
-        u64 si = warp_incl_sum64(s);
+        // block-wide exclusive sum scan of the per-thread sums
+        const u64 si = warp_incl_sum64(tsum);
         if (lane == 31) sh[w] = si;
         __syncthreads();
         if (w == 0) {
@@ -195,10 +211,14 @@ __global__ void __launch_bounds__(ST) rle_scan_kernel(const u64 *__restrict__ la
             if (lane == 31) sh[32] = vi;
         }
         __syncthreads();
-        u64 pre = carry_sum + sh[w] + si - s;
-        u64 tile_sum = sh[32];
+        u64 pre = carry_sum + sh[w] + si - tsum;
+        const u64 tile_sum = sh[32];
         __syncthreads();
-        if (ok) P[c] = pre;
+#pragma unroll
+        for (int k = 0; k < SI; k++) {
+            if (c0 + k < n_chunks) P[c0 + k] = pre;
+            pre += sv[k];
+        }
         carry_sum += tile_sum;
         carry_head = max(carry_head, tile_head);
     }
@@ -390,6 +410,18 @@ __global__ void __launch_bounds__(WPB * 32) crc_chunk_kernel(const u8 *__restric
     }
 }
 
+// acc -> CRC-32/BZIP2: fold in init and xorout.  One warp per block.
+__global__ void __launch_bounds__(WPB * 32) crc_finalize_kernel(const u32 *__restrict__ acc,
+                                                               const RleBlock *__restrict__ blocks, u32 n_blocks,
+                                                               u32 *__restrict__ crc)
+{
+    const u32 b = blockIdx.x * WPB + warp_id();
+    if (b >= n_blocks) return;
+    const u64 len = blocks[b].c - blocks[b].s;
+    const u32 p = warp_xpow8(len);
+    if (lane_id() == 0) crc[b] = acc[b] ^ gf_mul(0xFFFFFFFFu, p) ^ 0xFFFFFFFFu;
+}
+
 }  // namespace rle
 
 // ---------------------------------------------------------------------------------------
@@ -445,12 +477,22 @@ cudaError_t rle_summary_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunk
 
 cudaError_t rle_emit_launch(const uint8_t *d_in, uint64_t N, uint64_t c_begin, uint64_t c_end,
                             const uint64_t *d_oin, const uint64_t *d_P, const RleBlock *d_blocks,
-                            uint32_t n_blocks, uint8_t *d_out, uint32_t *d_crc_acc, cudaStream_t st)
+                            uint32_t n_blocks, uint8_t *d_out, cudaStream_t st)
 {
     if (c_end <= c_begin) return cudaSuccess;
     unsigned grid = (unsigned)((c_end - c_begin + rle::WPB - 1) / rle::WPB);
     rle::rle_emit_kernel<<<grid, rle::WPB * 32, 0, st>>>(d_in, N, c_begin, c_end, d_oin, d_P, d_blocks, n_blocks, d_out);
+    return cudaGetLastError();
+}
+
+// block CRCs (acc must be zeroed): chunk CRCs + combine, then init/xorout; crc[b] is final
+cudaError_t crc_launch(const uint8_t *d_in, uint64_t N, uint64_t c_begin, uint64_t c_end, const RleBlock *d_blocks,
+                       uint32_t n_blocks, uint32_t *d_crc_acc, uint32_t *d_crc, cudaStream_t st)
+{
+    if (c_end <= c_begin || n_blocks == 0) return cudaSuccess;
+    unsigned grid = (unsigned)((c_end - c_begin + rle::WPB - 1) / rle::WPB);
     rle::crc_chunk_kernel<<<grid, rle::WPB * 32, 0, st>>>(d_in, N, c_begin, c_end, d_blocks, n_blocks, d_crc_acc);
+    rle::crc_finalize_kernel<<<(n_blocks + rle::WPB - 1) / rle::WPB, rle::WPB * 32, 0, st>>>(d_crc_acc, d_blocks, n_blocks, d_crc);
     return cudaGetLastError();
 }
 
