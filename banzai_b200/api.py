@@ -83,7 +83,8 @@ class Context:
         try:
             if cons.value != a.size:
                 raise BanzaiError(_ffi.EINTERNAL, "short encode")
-            return C.string_at(out.value, olen.value)
+            # (ctypes.string_at takes a C int length: it would truncate streams >= 2 GiB)
+            return bytes((C.c_ubyte * olen.value).from_address(out.value))
         finally:
             lib.bnz_free(self._h, out)
 

@@ -415,6 +415,9 @@ __device__ RerankOut rerank(Smem<T> &sm, const u64 *src, u32 lo, u32 hi, u32 cou
                 nrv[k] = r1 + (p_key - p_grp);
                 bool single = hk && (j + 1 == count || key[k + 2] != key[k + 1]);
                 flg[k] = 1u | (single ? 2u : 0u);
+                // a record that stays in the first subgroup of its old group keeps its rank: its
+                // rank[] entry is already correct, skip the (random, 32-byte-sector) store
+                if (!single && !initial && nrv[k] == r1) flg[k] |= 4u;
                 if (!single) n_active++;
                 if (hk && !hg) n_split++;
             }
@@ -432,7 +435,7 @@ __device__ RerankOut rerank(Smem<T> &sm, const u64 *src, u32 lo, u32 hi, u32 cou
                     rank[id] = nrv[k] | DONE;
                     bwt_out[nrv[k]] = (u8)sb[k];
                     if (id == 0) *ptr_out = nrv[k];
-                } else {
+                } else if (!(flg[k] & 4u)) {
                     rank[id] = nrv[k];
                 }
             }

@@ -65,6 +65,7 @@ struct __align__(128) Smem {
     u64 mbar;                                             // mbarrier of the TMA tile pipeline
     u32 scratch[40];
     u32 s_count;                                          // records appended by build_*
+    u32 s_list;                                           // active-list length appended by rerank
     u32 s_block;                                          // claimed block id
     u32 s_flags[8];
     u8 present[256];                                      // has_byte
@@ -92,21 +93,26 @@ __device__ __forceinline__ void hist_add(Smem<BITS> &sm, u64 rec)
 }
 
 // Round 0: key = the five bytes S[i..i+5) (cyclic), big-endian, so h = 5 afterwards.
+// S is 16-byte aligned and padded to 16 bytes, so two aligned 32-bit loads cover any 5-byte window.
 template <int BITS>
 __device__ void build_initial(Smem<BITS> &sm, const u8 *__restrict__ S, u32 n, u64 *dst)
 {
     hist_clear(sm);
     for (int i = threadIdx.x; i < 256; i += T) sm.present[i] = 0;
     __syncthreads();
+    const u32 *S32 = reinterpret_cast<const u32 *>(S);
     for (u32 base = 0; base < n; base += TILE) {
 #pragma unroll
         for (int k = 0; k < K; k++) {
             u32 i = base + k * T + threadIdx.x;
             if (i < n) {
                 u64 key = 0;
-                if (i + 5 <= n) {
-#pragma unroll
-                    for (int j = 0; j < 5; j++) key = (key << 8) | S[i + j];
+                if (i + 8 <= n) {
+                    const u32 w0 = __ldg(S32 + (i >> 2)), w1 = __ldg(S32 + (i >> 2) + 1);
+                    const u32 sh = (i & 3) * 8;
+                    const u32 lo = __funnelshift_r(w0, w1, sh);            // bytes i .. i+3 (little endian)
+                    const u32 b4 = (w1 >> sh) & 0xffu;                     // byte i+4
+                    key = ((u64)__byte_perm(lo, 0, 0x0123) << 8) | b4;
                 } else {
                     u32 q = i;
                     for (int j = 0; j < 5; j++) {
@@ -184,6 +190,49 @@ __device__ __forceinline__ u32 match_digit(u32 d)
         peers &= bit ? vote : ~vote;
     }
     return peers;
+}
+
+// Round h when few rotations are still active: the previous re-rank left the list of active
+// (new rank, idx) pairs, so only those are touched instead of scanning all n ranks.
+template <int BITS>
+__device__ void build_round_list(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h, const u64 *alist, u32 cnt,
+                                 u64 *dst)
+{
+    hist_clear(sm);
+    const u32 hm = h % n;
+    for (u32 base = 0; base < cnt; base += TILE) {
+        u64 e[K];
+        u32 r2[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            u32 j = base + k * T + threadIdx.x;
+            e[k] = (j < cnt) ? alist[j] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            u32 j = base + k * T + threadIdx.x;
+            r2[k] = 0;
+            if (j < cnt) {
+                u32 q = ((u32)e[k] & IDX_MASK) + hm;
+                if (q >= n) q -= n;
+                r2[k] = rank[q] & RANK_MASK;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            u32 j = base + k * T + threadIdx.x;
+            if (j < cnt) {
+                const u32 idx = (u32)e[k] & IDX_MASK;
+                const u64 r1 = e[k] >> IDX_BITS;
+                const u64 rec = (r1 << (IDX_BITS + 20)) | ((u64)r2[k] << IDX_BITS) | idx;
+                dst[j] = rec;
+                hist_add(sm, rec);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sm.s_count = cnt;
+    __syncthreads();
 }
 
 // One LSD pass over `count` records: src -> dst by digit `pass`.
@@ -329,9 +378,11 @@ struct RerankOut {
 template <int BITS>
 __device__ RerankOut rerank(Smem<BITS> &sm, const u64 *src, u32 count, bool initial,
                             const u8 *__restrict__ S, u32 n, u32 *rank,
-                            u8 *__restrict__ bwt_out, u32 *ptr_out)
+                            u8 *__restrict__ bwt_out, u32 *ptr_out, u64 *alist)
 {
     const u32 tid = threadIdx.x;
+    if (tid == 0) sm.s_list = 0;
+    __syncthreads();
     u32 carry_grp = 0, carry_key = 0;       // 1-based positions of the latest heads so far
     u32 n_active = 0, n_split = 0;
     const u64 grp_mask = initial ? 0ull : ((u64)RANK_MASK << 20);   // bits of r1 inside key40
@@ -386,6 +437,9 @@ __device__ RerankOut rerank(Smem<BITS> &sm, const u64 *src, u32 count, bool init
                 nrv[k] = r1 + (p_key - p_grp);
                 bool single = hk && (j + 1 == count || key[k + 2] != key[k + 1]);
                 flg[k] = 1u | (single ? 2u : 0u);
+                // a record that stays in the first subgroup of its old group keeps its rank: its
+                // rank[] entry is already correct, skip the (random, 32-byte-sector) store
+                if (!single && !initial && nrv[k] == r1) flg[k] |= 4u;
                 if (!single) n_active++;
                 if (hk && !hg) n_split++;
             }
@@ -395,6 +449,20 @@ __device__ RerankOut rerank(Smem<BITS> &sm, const u64 *src, u32 count, bool init
             sb[k] = 0;
             if (flg[k] & 2u) sb[k] = S[idx[k] == 0 ? n - 1 : idx[k] - 1];
         }
+        if (alist) {
+            // compact (new rank, idx) of the rotations that stay active (order is irrelevant)
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const bool act = (flg[k] & 3u) == 1u;
+                const u32 m = __ballot_sync(0xffffffffu, act);
+                if (m) {
+                    u32 wbase = 0;
+                    if (lane_id() == 0) wbase = atomicAdd(&sm.s_list, (u32)__popc(m));
+                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    if (act) alist[wbase + __popc(m & lanemask_lt())] = ((u64)nrv[k] << IDX_BITS) | idx[k];
+                }
+            }
+        }
 #pragma unroll
         for (int k = 0; k < K; k++) {
             if (flg[k] & 1u) {
@@ -403,7 +471,7 @@ __device__ RerankOut rerank(Smem<BITS> &sm, const u64 *src, u32 count, bool init
                     rank[id] = nrv[k] | DONE;
                     bwt_out[nrv[k]] = (u8)sb[k];
                     if (id == 0) *ptr_out = nrv[k];
-                } else {
+                } else if (!(flg[k] & 4u)) {
                     rank[id] = nrv[k];
                 }
             }
@@ -504,10 +572,13 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
         u32 count = n;
         bool initial = true;
         bool tied = false;
+        const u64 *alist = nullptr;           // active list left by the previous re-rank (or null)
+        u32 alist_cnt = 0;
 
         while (count > 0 && rounds < MAX_ROUNDS) {
             t0 = clock64();
             if (initial) build_initial<BITS>(sm, S, n, bufA);
+            else if (alist) build_round_list<BITS>(sm, rank, n, h, alist, alist_cnt, bufA);
             else build_round<BITS>(sm, rank, n, h, bufA);
             count = sm.s_count;
             t1 = clock64();
@@ -535,8 +606,13 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
 
             t0 = clock64();
             cyc_radix += t0 - t1;
-            RerankOut ro = rerank<BITS>(sm, src, count, initial, S, n, rank, bwt_out, ptr_out);
+            // few active rotations: let the re-rank leave their list in the tail of the free buffer
+            // (the next key build writes < n/8 records at the front of bufA, the list sits at the end)
+            u64 *next_list = (!initial && (u64)count * 8 < n) ? dst + (a.ws_stride - count) : nullptr;
+            RerankOut ro = rerank<BITS>(sm, src, count, initial, S, n, rank, bwt_out, ptr_out, next_list);
             __syncthreads();
+            alist = next_list;
+            alist_cnt = sm.s_list;
             cyc_rerank += clock64() - t0;
             if (ro.active > 0 && ro.splits == 0 && !initial) {
                 finalize_ties<BITS>(sm, src, count, S, n, rank, bwt_out, ptr_out);

@@ -397,22 +397,27 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
     if (!blocks || !blk_off || !blk_len || !bwt_out || !ptr_out || !has_byte_out) return BNZ_EINVAL;
     Device &d = ctx->devs[0];
     CK(ctx, cudaSetDevice(d.id));
+    // device layout: every block image 16-byte aligned (what the pipeline guarantees the kernels)
+    std::vector<uint64_t> doff(n_blocks);
     size_t total = 0;
     uint32_t max_len = 0;
     for (size_t b = 0; b < n_blocks; b++) {
         if (blk_len[b] == 0 || blk_len[b] > (uint32_t)(100000 * level)) return BNZ_EINVAL;
-        total = std::max<size_t>(total, blk_off[b] + blk_len[b]);
+        doff[b] = total;
+        total += ((size_t)blk_len[b] + 15) & ~(size_t)15;
         max_len = std::max(max_len, blk_len[b]);
     }
-    CK(ctx, d.rle.ensure(total));
-    CK(ctx, d.bwt.ensure(total));
+    CK(ctx, d.rle.ensure(total + 16));
+    CK(ctx, d.bwt.ensure(total + 16));
     CK(ctx, d.blk_off.ensure(n_blocks * sizeof(uint64_t)));
     CK(ctx, d.blk_len.ensure(n_blocks * sizeof(uint32_t)));
     CK(ctx, d.ptr.ensure(n_blocks * sizeof(uint32_t)));
     CK(ctx, d.has_byte.ensure(n_blocks * 256));
     CK(ctx, d.bwt_stats.ensure(n_blocks * sizeof(BwtStats)));
-    CK(ctx, cudaMemcpyAsync(d.rle.p, blocks, total, cudaMemcpyHostToDevice, d.stream));
-    CK(ctx, cudaMemcpyAsync(d.blk_off.p, blk_off, n_blocks * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemsetAsync(d.rle.p, 0, total + 16, d.stream));
+    for (size_t b = 0; b < n_blocks; b++)
+        CK(ctx, cudaMemcpyAsync(d.rle.as<uint8_t>() + doff[b], blocks + blk_off[b], blk_len[b], cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemcpyAsync(d.blk_off.p, doff.data(), n_blocks * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
     CK(ctx, cudaMemcpyAsync(d.blk_len.p, blk_len, n_blocks * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
     cudaEvent_t e0, e1;
     CK(ctx, cudaEventCreate(&e0));
@@ -423,7 +428,8 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
                             d.has_byte.as<uint8_t>(), d.bwt_stats.as<BwtStats>());
     if (rc != BNZ_OK) return rc;
     CK(ctx, cudaEventRecord(e1, d.stream));
-    CK(ctx, cudaMemcpyAsync(bwt_out, d.bwt.p, total, cudaMemcpyDeviceToHost, d.stream));
+    for (size_t b = 0; b < n_blocks; b++)
+        CK(ctx, cudaMemcpyAsync(bwt_out + blk_off[b], d.bwt.as<uint8_t>() + doff[b], blk_len[b], cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaMemcpyAsync(ptr_out, d.ptr.p, n_blocks * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaMemcpyAsync(has_byte_out, d.has_byte.p, n_blocks * 256, cudaMemcpyDeviceToHost, d.stream));
     std::vector<BwtStats> st(n_blocks);
