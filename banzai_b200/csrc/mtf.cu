@@ -326,9 +326,9 @@ __global__ void __launch_bounds__(T4) mtf_rle2_kernel(MtfArgs a)
                         }
                     }
                 }
-                // warp-aggregated histogram of the index symbols
-                u32 peers = __match_any_sync(0xffffffffu, sym);
-                if (sym != 0xffffffffu && lane_id() == (u32)(__ffs(peers) - 1)) atomicAdd(&hist[sym], (u32)__popc(peers));
+                // histogram of the index symbols (shared atomics: ~1-3 SM-cycles per warp-op on this
+                // part, whereas match.any costs ~1000 cycles per call — tools/micro/match_bench.cu)
+                if (sym != 0xffffffffu) atomicAdd(&hist[sym], 1u);
             }
         }
         runa = __reduce_add_sync(0xffffffffu, runa);

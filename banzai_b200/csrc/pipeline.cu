@@ -228,7 +228,8 @@ extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
         return BNZ_OK;
     }
     if (!strcmp(key, "bwt_lpt")) {
-        ctx->bwt_lpt = value != 0;
+        if (value < 0 || value > 2) return BNZ_EINVAL;
+        ctx->bwt_lpt = (int)value;       // 0 off, 1 longest first, 2 light blocks last
         return BNZ_OK;
     }
     if (!strcmp(key, "bwt_cluster_below")) {
@@ -370,8 +371,22 @@ static int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t
         CK(ctx, cudaMemcpyAsync(score.data(), d.bwt_score.p, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, d.stream));
         CK(ctx, cudaStreamSynchronize(d.stream));
         ctx->last_scores = score;
-        for (uint32_t i = 0; i < n_blocks; i++) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return score[x] > score[y]; });
+        if (ctx->bwt_lpt == 1) {
+            // full longest-first order
+            for (uint32_t i = 0; i < n_blocks; i++) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return score[x] > score[y]; });
+        } else {
+            // "light tail": keep the natural (type-interleaved) order, but move the `grid` cheapest
+            // blocks to the end of the queue so that the last wave consists of short blocks
+            std::vector<uint32_t> by(n_blocks);
+            for (uint32_t i = 0; i < n_blocks; i++) by[i] = i;
+            std::stable_sort(by.begin(), by.end(), [&](uint32_t x, uint32_t y) { return score[x] < score[y]; });
+            std::vector<uint8_t> tail(n_blocks, 0);
+            for (int i = 0; i < grid; i++) tail[by[i]] = 1;
+            uint32_t k = 0;
+            for (uint32_t i = 0; i < n_blocks; i++) if (!tail[i]) order[k++] = i;
+            for (uint32_t i = 0; i < n_blocks; i++) if (tail[i]) order[k++] = i;
+        }
         CK(ctx, cudaMemcpyAsync(d.bwt_order.p, order.data(), (size_t)n_blocks * 4, cudaMemcpyHostToDevice, d.stream));
         CK(ctx, cudaStreamSynchronize(d.stream));      // `order` is a stack vector
         a.order = d.bwt_order.as<uint32_t>();

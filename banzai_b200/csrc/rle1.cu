@@ -13,6 +13,8 @@
 // fresh run of length t.  The device produces P and o at 1 KiB chunk granularity; the host
 // walks the (inherently sequential) cut chain with a binary search + <= 2 KiB byte scan per
 // block; a second kernel then emits every block's RLE1 bytes position-parallel.
+#include <string.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -508,6 +510,16 @@ int rle_walk_cuts(const uint8_t *in, uint64_t N, int level, const uint64_t *P, c
     blocks.clear();
     uint64_t s = 0, rle_off = 0;
 
+    // eight bytes at once when no byte equals its predecessor (the common case outside runs):
+    // each of them starts a run, costs 1, and leaves the run offset at 1
+    auto no_adjacent_equal8 = [&](uint64_t i) -> bool {       // requires 1 <= i and i + 8 <= N
+        uint64_t a, b;
+        memcpy(&a, in + i, 8);
+        memcpy(&b, in + i - 1, 8);
+        uint64_t x = a ^ b;                                    // zero byte <=> in[i+k] == in[i+k-1]
+        return (((x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull) == 0);
+    };
+
     // P and run-offset (mod 255) at an arbitrary position x, scanning from its chunk start
     auto p_at = [&](uint64_t x, uint32_t &r_out) -> uint64_t {
         uint64_t c = x / CHB;
@@ -515,10 +527,17 @@ int rle_walk_cuts(const uint8_t *in, uint64_t N, int level, const uint64_t *P, c
         uint64_t i = c * CHB;
         uint64_t p = P[c];
         uint32_t r = (uint32_t)(o_in[c] % 255);
-        for (; i < x; i++) {
+        while (i < x) {
+            if (i >= 1 && i + 8 <= x && no_adjacent_equal8(i)) {
+                p += 8;
+                r = 1;
+                i += 8;
+                continue;
+            }
             if (i == 0 || in[i] != in[i - 1]) r = 0;
             p += need_of(r);
             r = (r == 254) ? 0 : r + 1;
+            i++;
         }
         r_out = r;
         return p;
@@ -564,8 +583,26 @@ int rle_walk_cuts(const uint8_t *in, uint64_t N, int level, const uint64_t *P, c
             uint32_t r = 0;
             const uint64_t Pe0 = p_at(e0, r);
             const uint64_t target = Pe0 + B;
-            // last chunk start with P <= target
+            // last chunk start with P <= target.  P grows by about one per input byte on ordinary
+            // data, so guess the chunk and gallop from there (a plain binary search over the whole
+            // table costs ~20 cache misses per block, which dominates at level 1)
             uint64_t c_lo = e0 / CHB, c_hi = n_chunks + 1;       // P[c_lo] <= target (P[c_lo] <= Pe0)
+            {
+                uint64_t g = c_lo + (target - P[c_lo]) / CHB;
+                if (g <= c_lo) g = c_lo + 1;
+                if (g > n_chunks) g = n_chunks;
+                if (g > c_lo && P[g] <= target) {
+                    c_lo = g;
+                    uint64_t step = 1;
+                    while (c_lo + step <= n_chunks && P[c_lo + step] <= target) { c_lo += step; step *= 2; }
+                    c_hi = std::min(c_lo + step, n_chunks + 1);
+                } else if (g > c_lo) {
+                    c_hi = g;
+                    uint64_t step = 1;
+                    while (c_hi > c_lo + step && P[c_hi - step] > target) { c_hi -= step; step *= 2; }
+                    if (c_hi > c_lo + step) c_lo = c_hi - step;
+                }
+            }
             while (c_hi - c_lo > 1) {
                 uint64_t mid = (c_lo + c_hi) / 2;
                 if (P[mid] <= target) c_lo = mid; else c_hi = mid;
@@ -578,12 +615,19 @@ int rle_walk_cuts(const uint8_t *in, uint64_t N, int level, const uint64_t *P, c
                 uint64_t i, p;
                 if (c_lo == e0 / CHB) { i = e0; p = Pe0; }
                 else { i = c_lo * CHB; p = P[c_lo]; r = (uint32_t)(o_in[c_lo] % 255); }
-                for (; i < N; i++) {
+                while (i < N) {
+                    if (i >= 1 && i + 8 <= N && p + 8 <= target && no_adjacent_equal8(i)) {
+                        p += 8;
+                        r = 1;
+                        i += 8;
+                        continue;
+                    }
                     if (i == 0 || in[i] != in[i - 1]) r = 0;
                     uint32_t nd = need_of(r);
                     if (p + nd > target) break;
                     p += nd;
                     r = (r == 254) ? 0 : r + 1;
+                    i++;
                 }
                 cut = i;
                 pc = p;

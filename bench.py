@@ -36,6 +36,8 @@ WORKLOADS = {
     "text-4GiB-L1": ("text", 4 << 30, 1, corpus.SEED_C4),
     "random-4GiB-L9": ("random", 4 << 30, 9, corpus.SEED_C5),
     "mixed-256MiB-L9": ("mixed", 256 << 20, 9, corpus.SEED_C2),
+    "random-1GiB-L9": ("random", 1 << 30, 9, corpus.SEED_C5),
+    "text-1GiB-L1": ("text", 1 << 30, 1, corpus.SEED_C4),
 }
 
 
@@ -49,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--radix-bits", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=1, help="concurrent block batches per GPU")
+    ap.add_argument("--set", action="append", default=[], help="ctx tunable key=value (repeatable)")
     return ap.parse_args()
 
 
@@ -201,6 +204,9 @@ def run_b200(args, kind, size, level, seed):
     ctx = banzai_b200.Context(devices=[local] * args.lanes)
     if args.radix_bits:
         ctx.set("bwt_radix_bits", args.radix_bits)
+    for kv in args.set:
+        k, v = kv.split("=")
+        ctx.set(k, int(v))
 
     # pinned host input (the e2e arm copies from it every step), synthetic corpus per rank
     h_in = lib.bnz_host_alloc(size)
@@ -209,7 +215,7 @@ def run_b200(args, kind, size, level, seed):
     h_arr = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_uint8)), shape=(size,))
     corpus.by_name(kind, size, D.object_seed(seed, rank), out=h_arr)
     d_in = lib.bnz_device_alloc(ctx._h, size + 64)
-    out_cap = size // 2 + (64 << 20)
+    out_cap = size + size // 8 + (64 << 20)        # incompressible input grows by ~0.4 %
     d_out = lib.bnz_device_alloc(ctx._h, out_cap)
     if not d_in or not d_out:
         raise SystemExit("device allocation failed")
