@@ -39,7 +39,7 @@ cudaError_t rle_emit_launch(const uint8_t *d_in, uint64_t N, uint64_t c_begin, u
 cudaError_t crc_launch(const uint8_t *d_in, uint64_t N, uint64_t c_begin, uint64_t c_end, const RleBlock *d_blocks,
                        uint32_t n_blocks, uint32_t *d_crc_acc, uint32_t *d_crc, cudaStream_t st);
 int rle_walk_cuts(const uint8_t *in, uint64_t N, int level, const uint64_t *P, const uint64_t *o_in,
-                  uint64_t n_chunks, std::vector<RleBlock> &blocks);
+                  uint64_t n_chunks, std::vector<RleBlock> &blocks, bool final, uint64_t *consumed);
 
 // ---------------------------------------------------------------- K3/K4 BWT (bwt_sort.cu)
 

@@ -100,6 +100,8 @@ struct bnz_ctx {
     uint8_t *out_cache = nullptr;
     size_t out_cache_cap = 0;
     bool out_cache_lent = false;
+    uint8_t *out_big = nullptr;         // streaming-batch output (ordinary host memory), lent to the caller
+    size_t max_batch_bytes = (size_t)3 << 30;   // inputs above this are encoded in streaming batches
 };
 
 // worker threads of a multi-device encode record their error text in their own string
@@ -211,6 +213,7 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
         if (d.stream2) cudaStreamDestroy(d.stream2);
     }
     if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
+    free(ctx->out_big);
     delete ctx;
 }
 
@@ -225,6 +228,11 @@ extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
     if (!strcmp(key, "bwt_cluster")) {
         if (value < -1 || value > BWT_CLUSTER_MAX) return BNZ_EINVAL;
         ctx->bwt_cluster = (int)value;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "max_batch_bytes")) {
+        if (value < (1 << 20)) return BNZ_EINVAL;
+        ctx->max_batch_bytes = (size_t)value;
         return BNZ_OK;
     }
     if (!strcmp(key, "bwt_lpt")) {
@@ -495,9 +503,10 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
 // K1 part 1 on one device: chunk tables -> host -> cut walk.  Leaves P / o_in in d.h_P / d.h_oin
 // (host, pinned) and in d.ch_P / d.ch_oin (device).
 static int rle_plan(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const uint8_t *h_in, uint64_t N, int level,
-                    std::vector<RleBlock> &blocks)
+                    std::vector<RleBlock> &blocks, bool final = true, uint64_t *consumed = nullptr)
 {
     blocks.clear();
+    if (consumed) *consumed = 0;
     if (N == 0) return BNZ_OK;
     const uint64_t n_chunks = (N + RLE_CHUNK - 1) / RLE_CHUNK;
     CK(ctx, d.ch_lasthead.ensure(n_chunks * 8));
@@ -514,7 +523,7 @@ static int rle_plan(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const uint8_t 
     CK(ctx, cudaMemcpyAsync(d.h_P.p, d.ch_P.p, (n_chunks + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaMemcpyAsync(d.h_oin.p, d.ch_oin.p, n_chunks * 8, cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaStreamSynchronize(d.stream));
-    if (rle_walk_cuts(h_in, N, level, d.h_P.as<uint64_t>(), d.h_oin.as<uint64_t>(), n_chunks, blocks) != 0)
+    if (rle_walk_cuts(h_in, N, level, d.h_P.as<uint64_t>(), d.h_oin.as<uint64_t>(), n_chunks, blocks, final, consumed) != 0)
         return fail(ctx, BNZ_EINTERNAL, "RLE1 cut walk failed");
     return BNZ_OK;
 }
@@ -1003,21 +1012,32 @@ static void add_stats(bnz_stats &st, const Shard &sh)
 
 static void finish_stats(bnz_ctx *ctx, std::vector<Shard> &shards, bool have_d2h)
 {
+    // per batch: max over the shards (they run concurrently); batches add up
     bnz_stats &st = ctx->stats;
+    float h2d = 0, rle = 0, bwt = 0, mtf = 0, huff = 0, pack = 0, d2h = 0, total = 0;
     for (Shard &sh : shards) {
+        if (sh.blocks.empty()) continue;
         Device &d = *sh.d;
         cudaSetDevice(d.id);
         auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, d.ev[a], d.ev[b]); return ms; };
-        st.h2d_ms = std::max(st.h2d_ms, el(0, 1));
-        st.rle_ms = std::max(st.rle_ms, el(1, 2));
-        st.bwt_ms = std::max(st.bwt_ms, el(2, 3));
-        st.mtf_ms = std::max(st.mtf_ms, el(3, 4));
-        st.huff_ms = std::max(st.huff_ms, el(4, 5));
-        st.pack_ms = std::max(st.pack_ms, el(5, 6));
-        if (have_d2h) st.d2h_ms = std::max(st.d2h_ms, el(6, 7));
-        st.total_ms = std::max(st.total_ms, el(0, have_d2h ? 7 : 6));
+        h2d = std::max(h2d, el(0, 1));
+        rle = std::max(rle, el(1, 2));
+        bwt = std::max(bwt, el(2, 3));
+        mtf = std::max(mtf, el(3, 4));
+        huff = std::max(huff, el(4, 5));
+        pack = std::max(pack, el(5, 6));
+        if (have_d2h) d2h = std::max(d2h, el(6, 7));
+        total = std::max(total, el(0, have_d2h ? 7 : 6));
     }
-    st.n_devices = (uint32_t)shards.size();
+    st.h2d_ms += h2d;
+    st.rle_ms += rle;
+    st.bwt_ms += bwt;
+    st.mtf_ms += mtf;
+    st.huff_ms += huff;
+    st.pack_ms += pack;
+    st.d2h_ms += d2h;
+    st.total_ms += total;
+    st.n_devices = std::max<uint32_t>(st.n_devices, (uint32_t)shards.size());
     st.bwt_radix_bits = (uint32_t)ctx->radix_bits;
 }
 
@@ -1057,11 +1077,14 @@ static std::vector<uint32_t> split_blocks(const std::vector<RleBlock> &blocks, s
     return cut;
 }
 
-// The whole path.  h_in: host input; d_in0: optional device copy already resident on device 0
-// (single-device contexts only).  Leaves every shard's bits in its device's d.out and returns
-// the stream layout; the callers move the bytes.
+// One batch of the path: the blocks that can be cut from h_in[0, N).  d_in0: optional device copy
+// already resident on device 0.  `final`: no input follows (otherwise the trailing incomplete
+// block is left for the next batch; *consumed tells where it starts).  `bit_base`: bit offset of
+// the batch's first block in the stream.  Leaves every shard's bits in its device's d.out and
+// returns the layout; the callers move the bytes.
 static int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, size_t N, int level,
-                      std::vector<Shard> &shards, std::vector<uint32_t> &crcs, uint64_t *total_bits)
+                      std::vector<Shard> &shards, std::vector<uint32_t> &crcs, uint64_t *total_bits,
+                      bool final = true, uint64_t bit_base = 32, uint64_t *consumed = nullptr)
 {
     Device &d0 = ctx->devs[0];
     bnz_stats &st = ctx->stats;
@@ -1078,8 +1101,13 @@ static int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, s
     CK(ctx, cudaEventRecord(d0.ev[1], d0.stream));
 
     std::vector<RleBlock> blocks;
-    int rc = rle_plan(ctx, d0, d_in, h_in, N, level, blocks);
+    int rc = rle_plan(ctx, d0, d_in, h_in, N, level, blocks, final, consumed);
     if (rc != BNZ_OK) return rc;
+    if (blocks.empty()) {               // (non-final batch shorter than one block)
+        shards.clear();
+        *total_bits = bit_base;
+        return BNZ_OK;
+    }
 
     CK(ctx, cudaEventRecord(d0.ev[8], d0.stream));       // input + chunk tables resident on device 0
     const size_t n_dev = std::min(ctx->devs.size(), std::max<size_t>(1, blocks.size()));
@@ -1150,8 +1178,7 @@ static int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, s
     }
 
     // bit offsets of the shards (blocks are concatenated at bit granularity, lib.rs:101-126 + out.rs)
-    uint64_t bits = 32;
-    crcs.clear();
+    uint64_t bits = bit_base;
     for (Shard &sh : shards) {
         sh.bit_base = bits;
         bits += sh.block_bits;
@@ -1159,6 +1186,47 @@ static int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, s
     }
     *total_bits = bits;
     for (Shard &sh : shards) add_stats(st, sh);
+    return BNZ_OK;
+}
+
+// pack every shard of a batch at its bit phase and copy it to host memory `o` (the stream buffer,
+// byte 0 = stream byte 0).  `stream_start`: the batch begins right after the 32-bit stream header,
+// so its first word is not shared with earlier data.
+static int pack_and_download(bnz_ctx *ctx, std::vector<Shard> &shards, uint8_t *o, bool stream_start)
+{
+    std::vector<uint32_t> first_word(shards.size(), 0);
+    for (size_t g = 0; g < shards.size(); g++) {
+        Shard &sh = shards[g];
+        if (sh.blocks.empty()) continue;
+        Device &d = *sh.d;
+        CK(ctx, cudaSetDevice(d.id));
+        size_t bytes = 0;
+        int rc = shard_pack(ctx, sh, &bytes);
+        if (rc != BNZ_OK) return rc;
+        const size_t w0 = (size_t)(sh.bit_base >> 5) * 4;
+        if (g == 0 && stream_start) {
+            CK(ctx, cudaMemcpyAsync(o + w0, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
+        } else {
+            CK(ctx, cudaMemcpyAsync(&first_word[g], d.out.p, 4, cudaMemcpyDeviceToHost, d.stream));
+            if (bytes > 4)
+                CK(ctx, cudaMemcpyAsync(o + w0 + 4, d.out.as<uint8_t>() + 4, bytes - 4, cudaMemcpyDeviceToHost, d.stream));
+        }
+        CK(ctx, cudaEventRecord(d.ev[7], d.stream));
+        ctx->stats.d2h_bytes += bytes;
+    }
+    for (Shard &sh : shards) {
+        if (sh.blocks.empty()) continue;
+        CK(ctx, cudaSetDevice(sh.d->id));
+        CK(ctx, cudaStreamSynchronize(sh.d->stream));
+    }
+    // merge the words shared with the previous shard / batch
+    for (size_t g = 0; g < shards.size(); g++) {
+        if (shards[g].blocks.empty() || (g == 0 && stream_start)) continue;
+        uint8_t *w = o + (size_t)(shards[g].bit_base >> 5) * 4;
+        const uint8_t *f = reinterpret_cast<const uint8_t *>(&first_word[g]);
+        if ((shards[g].bit_base & 31) == 0) memcpy(w, f, 4);
+        else for (int k = 0; k < 4; k++) w[k] |= f[k];
+    }
     return BNZ_OK;
 }
 
@@ -1171,70 +1239,93 @@ extern "C" int bnz_encode(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int le
     if (consumed) *consumed = 0;
     if (level < 1 || level > 9) return fail(ctx, BNZ_EINVAL, "level must be in 1..=9 (lib/lib.rs:89)");
     if (in_len && !in) return BNZ_EINVAL;
-    if (ctx->out_cache_lent) return fail(ctx, BNZ_EINVAL, "previous output not released with bnz_free");
+    if (ctx->out_cache_lent || ctx->out_big) return fail(ctx, BNZ_EINVAL, "previous output not released with bnz_free");
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.in_bytes = in_len;
 
     uint64_t total_bits = 32;
     std::vector<uint32_t> crcs;
-    std::vector<Shard> shards;
-    if (in_len > 0) {
-        int rc = encode_all(ctx, in, nullptr, in_len, level, shards, crcs, &total_bits);
-        if (rc != BNZ_OK) return rc;
-    }
-    const size_t nbytes = (size_t)((total_bits + 80 + 7) / 8);
-    int rc = ensure_out_cache(ctx, nbytes + 8);
-    if (rc != BNZ_OK) return rc;
-    uint8_t *o = ctx->out_cache;
+    uint8_t *o = nullptr;
+    size_t nbytes = 0;
 
-    if (in_len > 0) {
-        // every shard packs at its bit phase and copies straight into the output; a word shared
-        // by two shards is OR-ed on the host afterwards
-        std::vector<uint32_t> first_word(shards.size(), 0);
-        for (size_t g = 0; g < shards.size(); g++) {
-            Shard &sh = shards[g];
-            if (sh.blocks.empty()) continue;
-            Device &d = *sh.d;
-            CK(ctx, cudaSetDevice(d.id));
-            size_t bytes = 0;
-            rc = shard_pack(ctx, sh, &bytes);
+    if (in_len <= ctx->max_batch_bytes) {
+        // ---- one batch: the stream is assembled in the context's pinned buffer
+        std::vector<Shard> shards;
+        if (in_len > 0) {
+            int rc = encode_all(ctx, in, nullptr, in_len, level, shards, crcs, &total_bits);
             if (rc != BNZ_OK) return rc;
-            const size_t w0 = (size_t)(sh.bit_base >> 5) * 4;
-            if (g == 0) {
-                CK(ctx, cudaMemcpyAsync(o + w0, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
-            } else {
-                CK(ctx, cudaMemcpyAsync(&first_word[g], d.out.p, 4, cudaMemcpyDeviceToHost, d.stream));
-                if (bytes > 4)
-                    CK(ctx, cudaMemcpyAsync(o + w0 + 4, d.out.as<uint8_t>() + 4, bytes - 4, cudaMemcpyDeviceToHost, d.stream));
-            }
-            CK(ctx, cudaEventRecord(d.ev[7], d.stream));
-            ctx->stats.d2h_bytes += bytes;
         }
-        for (Shard &sh : shards) {
-            if (sh.blocks.empty()) continue;
-            CK(ctx, cudaSetDevice(sh.d->id));
-            CK(ctx, cudaStreamSynchronize(sh.d->stream));
+        nbytes = (size_t)((total_bits + 80 + 7) / 8);
+        int rc = ensure_out_cache(ctx, nbytes + 8);
+        if (rc != BNZ_OK) return rc;
+        o = ctx->out_cache;
+        if (in_len > 0) {
+            rc = pack_and_download(ctx, shards, o, true);
+            if (rc != BNZ_OK) return rc;
+            const size_t written = (size_t)((total_bits + 31) / 32) * 4;
+            if (written < nbytes + 8) memset(o + written, 0, nbytes + 8 - written);
+            finish_stats(ctx, shards, true);
+        } else {
+            memset(o, 0, nbytes + 8);
         }
-        // zero the tail the devices did not write, then merge the shared words
-        const size_t written = (size_t)((total_bits + 31) / 32) * 4;
-        if (written < nbytes + 8) memset(o + written, 0, nbytes + 8 - written);
-        for (size_t g = 1; g < shards.size(); g++) {
-            if (shards[g].blocks.empty()) continue;
-            uint8_t *w = o + (size_t)(shards[g].bit_base >> 5) * 4;
-            const uint8_t *f = reinterpret_cast<const uint8_t *>(&first_word[g]);
-            if ((shards[g].bit_base & 31) == 0) memcpy(w, f, 4);
-            else for (int k = 0; k < 4; k++) w[k] |= f[k];
-        }
-        finish_stats(ctx, shards, true);
+        ctx->out_cache_lent = true;
     } else {
-        memset(o, 0, nbytes + 8);
+        // ---- streaming batches (inputs larger than one device-resident batch): every batch runs
+        // the whole pipeline on the blocks that are complete inside its window; the trailing
+        // partial block is re-read by the next batch.  The stream grows in an ordinary host buffer.
+        size_t cap = 0, pos = 0, win = ctx->max_batch_bytes;
+        auto grow = [&](size_t need) -> bool {
+            if (need <= cap) return true;
+            size_t ncap = std::max(need + need / 4 + 4096, cap * 2);
+            uint8_t *p = static_cast<uint8_t *>(realloc(o, ncap));
+            if (!p) return false;
+            memset(p + cap, 0, ncap - cap);
+            o = p;
+            cap = ncap;
+            return true;
+        };
+        bool first = true;
+        while (pos < in_len) {
+            const size_t len = std::min(win, in_len - pos);
+            const bool final = pos + len == in_len;
+            std::vector<Shard> shards;
+            uint64_t used = 0, bits_after = total_bits;
+            int rc = encode_all(ctx, in + pos, nullptr, len, level, shards, crcs, &bits_after, final, total_bits, &used);
+            if (rc != BNZ_OK) {
+                free(o);
+                return rc;
+            }
+            if (shards.empty()) {               // window shorter than one block: widen it
+                if (final) break;
+                win *= 2;
+                continue;
+            }
+            if (!grow((size_t)((bits_after + 80 + 7) / 8) + 16)) {
+                free(o);
+                return fail(ctx, BNZ_ENOMEM, "output buffer");
+            }
+            rc = pack_and_download(ctx, shards, o, first);
+            if (rc != BNZ_OK) {
+                free(o);
+                return rc;
+            }
+            finish_stats(ctx, shards, true);
+            first = false;
+            total_bits = bits_after;
+            pos += final ? len : (size_t)used;
+        }
+        nbytes = (size_t)((total_bits + 80 + 7) / 8);
+        if (!grow(nbytes + 16)) {
+            free(o);
+            return fail(ctx, BNZ_ENOMEM, "output buffer");
+        }
+        ctx->out_big = o;
     }
     // stream header (lib.rs:18-22), footer (lib.rs:66-70), zero padding (out.rs:22-28)
     o[0] = 0x42; o[1] = 0x5A; o[2] = 0x68; o[3] = (uint8_t)('0' + level);
     put_bits_host(o, total_bits, 0x177245385090ull, 48);
     put_bits_host(o, total_bits + 48, fold_stream_crc(crcs), 32);
     ctx->stats.out_bytes = nbytes;
-    ctx->out_cache_lent = true;
     *out = o;
     *out_len = nbytes;
     if (consumed) *consumed = in_len;
@@ -1245,6 +1336,10 @@ extern "C" void bnz_free(bnz_ctx *ctx, uint8_t *p)
 {
     if (!ctx || !p) return;
     if (p == ctx->out_cache) ctx->out_cache_lent = false;
+    if (p == ctx->out_big) {
+        free(ctx->out_big);
+        ctx->out_big = nullptr;
+    }
 }
 
 extern "C" int bnz_encode_device(bnz_ctx *ctx, const void *d_in, const uint8_t *h_in, size_t in_len, int level,

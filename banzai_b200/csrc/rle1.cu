@@ -500,8 +500,11 @@ cudaError_t crc_launch(const uint8_t *d_in, uint64_t N, uint64_t c_begin, uint64
 
 // The sequential cut chain (the part of lib/lib.rs:101-126 + lib/rle.rs:121-240 that couples
 // consecutive blocks).  `in` is the host copy of the input, P/o_in the chunk tables.
+// `final` == false: more input follows after in[N-1] (streaming batches); a block whose cut is
+// only the end of the available data is then incomplete and is left to the next batch.
+// *consumed = input bytes covered by the returned blocks.
 int rle_walk_cuts(const uint8_t *in, uint64_t N, int level, const uint64_t *P, const uint64_t *o_in,
-                  uint64_t n_chunks, std::vector<RleBlock> &blocks)
+                  uint64_t n_chunks, std::vector<RleBlock> &blocks, bool final, uint64_t *consumed)
 {
     using rle::need_of;
     const uint64_t M = (uint64_t)100000 * level - 1;
@@ -639,10 +642,12 @@ int rle_walk_cuts(const uint8_t *in, uint64_t N, int level, const uint64_t *P, c
             bk.n = (uint32_t)(u0 + (pc - Pe0));
         }
         if (bk.c <= bk.s || bk.n == 0 || bk.n > M) return -1;
+        if (!final && bk.c >= N) break;          // ran out of data, not out of capacity
         blocks.push_back(bk);
         rle_off += (bk.n + 15) & ~15ull;         // keep every block's RLE1 image 16-byte aligned
         s = bk.c;
     }
+    if (consumed) *consumed = blocks.empty() ? 0 : blocks.back().c;
     return 0;
 }
 

@@ -49,7 +49,9 @@ BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
 
 /* tunables (call before encoding). keys: "bwt_cluster" (-1 auto | 0 one CTA per block | 2..16 CTAs
  * per block), "bwt_cluster_below" (auto threshold in blocks), "bwt_threads" (512|1024, cluster
- * kernel), "bwt_radix_bits" (8|10, one-CTA kernel), "bwt_ctas_per_sm" (0 = auto) */
+ * kernel), "bwt_radix_bits" (8|10, one-CTA kernel), "bwt_ctas_per_sm" (0 = auto),
+ * "max_batch_bytes" (inputs above this, default 3 GiB, are encoded in streaming batches so that
+ * device memory stays bounded; the stream bytes do not depend on it) */
 BNZ_API int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value);
 
 /* ---- the hot path --------------------------------------------------------------------

@@ -142,3 +142,22 @@ def test_lanes_on_one_gpu_and_device_resident_entry():
             assert back.tobytes() == want
             lib.bnz_device_free(c._h, d_in)
             lib.bnz_device_free(c._h, d_out)
+
+
+def test_streaming_batches_do_not_change_the_stream():
+    """inputs above max_batch_bytes are encoded batch by batch (bounded device memory); block cuts
+    and bit offsets must chain across batches exactly"""
+    import banzai_b200
+    rng = np.random.default_rng(4)
+    mixed = corpus.mixed(23 * 1000 * 1000 + 5)
+    runs = np.repeat(rng.integers(0, 3, 4000), rng.integers(1, 30000, 4000)).astype(np.uint8)[:30 * 1000 * 1000]
+    zeros_then_text = np.concatenate([np.zeros(20 << 20, np.uint8), corpus.text(3000000), np.zeros(9 << 20, np.uint8)])
+    with banzai_b200.Context(n_gpus=1) as one, banzai_b200.Context(n_gpus=1) as ctx:
+        ctx.set("max_batch_bytes", 4 << 20)
+        for data, level in ((mixed, 9), (mixed, 1), (runs, 9), (zeros_then_text, 9), (zeros_then_text, 1)):
+            want = one.encode_bytes(data, level)
+            got = ctx.encode_bytes(data, level)
+            assert got == want, (data.size, level)
+        small = corpus.text(100000)
+        assert ctx.encode_bytes(small, 9) == O.encode(small, 9)
+        assert ctx.encode_bytes(mixed[:9000000], 3) == O.encode(mixed[:9000000], 3)
