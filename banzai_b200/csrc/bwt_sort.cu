@@ -34,7 +34,10 @@
 namespace bnz {
 namespace bwt {
 
-constexpr int T = 512;               // threads per CTA
+#ifndef BWT_T
+#define BWT_T 512
+#endif
+constexpr int T = BWT_T;             // threads per CTA
 constexpr int NW = T / 32;           // warps per CTA
 constexpr int K = 8;                 // records per thread per tile
 constexpr int TILE = T * K;          // 4096 records = 32 KB
@@ -534,7 +537,7 @@ __device__ void finalize_ties(Smem<BITS> &sm, const u64 *src, u32 count,
 }
 
 template <int BITS>
-__global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
+__global__ void __launch_bounds__(T, 1024 / T) bwt_sort_kernel(BwtArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<BITS> &sm = *reinterpret_cast<Smem<BITS> *>(smem_raw);
