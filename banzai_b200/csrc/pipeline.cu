@@ -141,39 +141,36 @@ extern "C" const char *bnz_strerror(int code)
 
 extern "C" const char *bnz_last_error(const bnz_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
 
+extern "C" void bnz_ctx_destroy(bnz_ctx *ctx);
+
 extern "C" int bnz_ctx_create_on(bnz_ctx **out, const int *device_ids, int n_devices)
 {
     if (!out || !device_ids || n_devices <= 0) return BNZ_EINVAL;
     *out = nullptr;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return BNZ_ECUDA;
+    for (int i = 0; i < n_devices; i++)
+        if (device_ids[i] < 0 || device_ids[i] >= count) return BNZ_EINVAL;
     bnz_ctx *ctx = new bnz_ctx();
     memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->devs.reserve(n_devices);
     for (int i = 0; i < n_devices; i++) {
-        if (device_ids[i] < 0 || device_ids[i] >= count) {
-            delete ctx;
-            return BNZ_EINVAL;
-        }
-        Device d;
+        // a device id may repeat: every entry is an independent lane (own streams and arenas)
+        ctx->devs.emplace_back();
+        Device &d = ctx->devs.back();
         d.id = device_ids[i];
         cudaDeviceProp prop;
-        if (cudaSetDevice(d.id) != cudaSuccess || cudaGetDeviceProperties(&prop, d.id) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking) != cudaSuccess) {
-            delete ctx;
-            return BNZ_ECUDA;
-        }
-        if (prop.major < 10) {      // kernels are built for sm_100a only; fail loudly
-            delete ctx;
+        bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaGetDeviceProperties(&prop, d.id) == cudaSuccess &&
+                  prop.major >= 10 &&        // kernels are built for sm_100a only; fail loudly
+                  cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking) == cudaSuccess;
+        for (cudaEvent_t &e : d.ev)
+            if (ok && cudaEventCreate(&e) != cudaSuccess) ok = false;
+        if (!ok) {
+            bnz_ctx_destroy(ctx);
             return BNZ_ECUDA;
         }
         d.sm_count = prop.multiProcessorCount;
-        for (cudaEvent_t &e : d.ev)
-            if (cudaEventCreate(&e) != cudaSuccess) {
-                delete ctx;
-                return BNZ_ECUDA;
-            }
-        ctx->devs.push_back(d);
     }
     *out = ctx;
     return BNZ_OK;

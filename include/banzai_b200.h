@@ -40,7 +40,8 @@ enum {
 
 /* n_gpus: number of visible CUDA devices to shard blocks over (0 = all visible). */
 BNZ_API int bnz_ctx_create(bnz_ctx **out, int n_gpus);
-/* explicit device ordinals (e.g. {LOCAL_RANK} for one-process-per-GPU launches) */
+/* explicit device ordinals (e.g. {LOCAL_RANK} for one-process-per-GPU launches); an ordinal may
+ * repeat, each entry is then an independent lane on that GPU */
 BNZ_API int bnz_ctx_create_on(bnz_ctx **out, const int *device_ids, int n_devices);
 BNZ_API void bnz_ctx_destroy(bnz_ctx *ctx);
 BNZ_API const char *bnz_strerror(int code);
