@@ -74,9 +74,17 @@ __device__ __forceinline__ u32 match_digit(u32 d)
     u32 peers = 0xffffffffu;
 #pragma unroll
     for (int b = 0; b < BITS; b++) {
-        const u32 bit = (d >> b) & 1u;
-        const u32 vote = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? vote : ~vote;
+        asm("{\n"
+            ".reg .pred p;\n"
+            ".reg .b32 t, v;\n"
+            "and.b32 t, %1, %2;\n"
+            "setp.ne.u32 p, t, 0;\n"
+            "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
+            "@!p not.b32 v, v;\n"
+            "and.b32 %0, %0, v;\n"
+            "}\n"
+            : "+r"(peers)
+            : "r"(d), "r"(1u << b));
     }
     return peers;
 }

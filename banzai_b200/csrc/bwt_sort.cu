@@ -59,7 +59,7 @@ template <int BITS>
 struct __align__(128) Smem {
     u64 inbuf[TILE];                                      // TMA landing zone for the next tile
     u64 stage[TILE];                                      // tile reorder buffer
-    u16 whist[NW][Cfg<BITS>::BINS];                       // per-warp digit counts / offsets
+    u32 whist[NW][Cfg<BITS>::BINS];                       // per-warp digit counts / offsets
     u32 cursor[Cfg<BITS>::BINS];                          // running bucket cursors (global)
     u32 binoff[Cfg<BITS>::BINS];                          // exclusive bin offsets inside the tile
     u32 gbase[Cfg<BITS>::BINS];                           // cursor - binoff
@@ -185,12 +185,22 @@ __device__ void build_round(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h,
 template <int BITS>
 __device__ __forceinline__ u32 match_digit(u32 d)
 {
+    // peers = lanes whose digit equals mine: AND over the digit's bits of XNOR(ballot(bit), my bit).
+    // Inline PTX keeps it at and/setp + vote + predicated not + and per bit.
     u32 peers = 0xffffffffu;
 #pragma unroll
     for (int b = 0; b < BITS; b++) {
-        const u32 bit = (d >> b) & 1u;
-        const u32 vote = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? vote : ~vote;
+        asm("{\n"
+            ".reg .pred p;\n"
+            ".reg .b32 t, v;\n"
+            "and.b32 t, %1, %2;\n"
+            "setp.ne.u32 p, t, 0;\n"
+            "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
+            "@!p not.b32 v, v;\n"
+            "and.b32 %0, %0, v;\n"
+            "}\n"
+            : "+r"(peers)
+            : "r"(d), "r"(1u << b));
     }
     return peers;
 }
@@ -282,14 +292,22 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
         const u32 tile_n = min((u32)TILE, count - base);
         u64 rec[K];
         u32 rk[K];
-        for (int b = lane; b < BINS; b += 32) sm.whist[w][b] = 0;
+        {   // zero this warp's counter row with 16-byte stores
+            uint4 *row = reinterpret_cast<uint4 *>(sm.whist[w]);
+            for (int b = lane; b < BINS * 4 / 16; b += 32) row[b] = make_uint4(0, 0, 0, 0);
+        }
         mbar_wait(&sm.mbar, phase);
         phase ^= 1u;
         const u32 wl = w * (K * 32) + lane;
+        if (tile_n == TILE) {
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            u32 j = wl + k * 32;
-            rec[k] = (j < tile_n) ? sm.inbuf[j] : ~0ull;
+            for (int k = 0; k < K; k++) rec[k] = sm.inbuf[wl + k * 32];
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                u32 j = wl + k * 32;
+                rec[k] = (j < tile_n) ? sm.inbuf[j] : ~0ull;
+            }
         }
         __syncwarp();
 #pragma unroll
@@ -297,14 +315,12 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             const u32 d = digit_of<BITS>(rec[k], pass);
             const u32 peers = match_digit<BITS>(d);
             const u32 leader = 31 - __clz(peers);
+            // one shared atomic per digit group; its return value is the group's base.  Atomics of
+            // successive rows to the same counter execute in program order, so rows need no barrier.
             u32 bcount = 0;
-            if (lane == leader) {
-                bcount = sm.whist[w][d];
-                sm.whist[w][d] = (u16)(bcount + __popc(peers));
-            }
+            if (lane == leader) bcount = atomicAdd(&sm.whist[w][d], (u32)__popc(peers));
             bcount = __shfl_sync(0xffffffffu, bcount, leader);
             rk[k] = bcount + __popc(peers & lanemask_lt());
-            __syncwarp();
         }
         __syncthreads();                                        // B1: inbuf consumed, whist complete
 
@@ -325,7 +341,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
 #pragma unroll
                 for (int ww = 0; ww < NW; ww++) {
                     u32 v = sm.whist[ww][b];
-                    sm.whist[ww][b] = (u16)run;
+                    sm.whist[ww][b] = run;
                     run += v;
                 }
                 c[j] = run;
@@ -357,13 +373,21 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
         }
         __syncthreads();                                        // B3
 
+        if (tile_n == TILE) {
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            const u32 j = k * T + tid;
-            if (j < tile_n) {
+            for (int k = 0; k < K; k++) {
+                const u32 j = k * T + tid;
                 const u64 r = sm.stage[j];
-                const u32 d = digit_of<BITS>(r, pass);
-                dst[sm.gbase[d] + j] = r;
+                dst[sm.gbase[digit_of<BITS>(r, pass)] + j] = r;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const u32 j = k * T + tid;
+                if (j < tile_n) {
+                    const u64 r = sm.stage[j];
+                    dst[sm.gbase[digit_of<BITS>(r, pass)] + j] = r;
+                }
             }
         }
         // no barrier here: the next tile's B1 orders these reads before stage/whist are reused
