@@ -17,7 +17,7 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH)
 
-OK, EINVAL, ECUDA, ENOMEM, EINTERNAL = 0, 1, 2, 3, 4
+OK, EINVAL, ECUDA, ENOMEM, EINTERNAL, EIO = 0, 1, 2, 3, 4, 5
 
 
 class Stats(C.Structure):
@@ -64,6 +64,14 @@ lib.bnz_encode_device.argtypes = [_vp, _vp, _vp, _sz, C.c_int, _vp, _sz, _szp]
 lib.bnz_max_compressed_size.argtypes = [_sz]
 lib.bnz_max_compressed_size.restype = _sz
 lib.bnz_encode_file.argtypes = [_vp, C.c_char_p, C.c_char_p, _szp]
+SINK_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, _sz)
+lib.bnz_stream_open.argtypes = [_vp, C.c_int, SINK_FN, _vp, C.POINTER(_vp)]
+lib.bnz_stream_reserve.argtypes = [_vp, C.POINTER(_vp), _szp]
+lib.bnz_stream_commit.argtypes = [_vp, _sz]
+lib.bnz_stream_write.argtypes = [_vp, _vp, _sz]
+lib.bnz_stream_finish.argtypes = [_vp, _szp]
+lib.bnz_stream_close.argtypes = [_vp]
+lib.bnz_stream_close.restype = None
 lib.bnz_host_alloc.argtypes = [_sz]
 lib.bnz_host_alloc.restype = _vp
 lib.bnz_host_free.argtypes = [_vp]
@@ -85,5 +93,6 @@ EXPORTS = [
     "bnz_ctx_set", "bnz_encode", "bnz_free", "bnz_encode_device", "bnz_max_compressed_size",
     "bnz_encode_file", "bnz_host_alloc", "bnz_host_free", "bnz_device_alloc", "bnz_device_free",
     "bnz_memcpy_h2d", "bnz_memcpy_d2h", "bnz_get_stats", "bnz_stage_rle1", "bnz_stage_bwt",
-    "bnz_stage_mtf", "bnz_stage_huffman",
+    "bnz_stage_mtf", "bnz_stage_huffman", "bnz_stream_open", "bnz_stream_reserve", "bnz_stream_commit",
+    "bnz_stream_write", "bnz_stream_finish", "bnz_stream_close",
 ]

@@ -106,6 +106,54 @@ class Context:
                                           C.byref(olen)))
         return olen.value
 
+    def encode_stream(self, reader, writer, level, read_size=8 << 20):
+        """streaming `banzai::encode(reader, writer, level)` over bnz_stream_* : the reader fills
+        pinned windows in place (readinto when it has it) while the previous window is on the
+        GPU; stream bytes reach `writer.write` in order, on this thread.  Returns bytes read."""
+        if not (1 <= level <= 9):
+            raise BanzaiError(_ffi.EINVAL, f"level {level}")
+        sink_exc = []
+
+        def _sink(_user, data, n):
+            try:
+                writer.write(bytes((C.c_ubyte * n).from_address(data)))
+                return 0
+            except Exception as e:          # surfaces as BNZ_EIO; the Python exception is re-raised
+                sink_exc.append(e)
+                return 1
+
+        cb = _ffi.SINK_FN(_sink)
+        h = C.c_void_p()
+        self._check(lib.bnz_stream_open(self._h, level, cb, None, C.byref(h)))
+        try:
+            buf, cap, used = C.c_void_p(), C.c_size_t(), C.c_size_t()
+            readinto = getattr(reader, "readinto", None)
+            try:
+                while True:
+                    self._check(lib.bnz_stream_reserve(h, C.byref(buf), C.byref(cap)))
+                    want = min(cap.value, read_size)
+                    if readinto is not None:
+                        got = readinto(memoryview((C.c_ubyte * want).from_address(buf.value)).cast("B"))
+                        got = 0 if got is None else got
+                    else:
+                        chunk = reader.read(want)
+                        got = len(chunk)
+                        if got:
+                            C.memmove(buf, chunk, got)
+                    if got == 0:
+                        break
+                    self._check(lib.bnz_stream_commit(h, got))
+                self._check(lib.bnz_stream_finish(h, C.byref(used)))
+            except BanzaiError:
+                if sink_exc:
+                    raise sink_exc[0]
+                raise
+            if hasattr(writer, "flush"):
+                writer.flush()
+            return used.value
+        finally:
+            lib.bnz_stream_close(h)
+
     # ---- stage seams ----------------------------------------------------------------
     def stage_bwt(self, blocks, level=9, with_stats=False):
         """`bwt::bwt` (lib/bwt.rs:526) on a list of byte blocks -> [(bwt, ptr, has_byte)]"""
@@ -223,17 +271,13 @@ def encode_bytes(data, level=9):
 def encode(reader, writer, level):
     """banzai::encode(reader, BufWriter, level) -> usize  (reference lib/lib.rs:84-132).
 
-    `reader` is any object with .read(); `writer` any object with .write() (and optionally
-    .flush()).  Like the reference it returns the number of input bytes encoded, and it
+    `reader` is any object with .readinto() or .read(n); `writer` any object with .write() (and
+    optionally .flush()).  The input is streamed window by window (include/banzai_b200.h,
+    bnz_stream_*), never held whole.  Like the reference it returns the number of input bytes encoded, and it
     rejects level outside 1..=9 (the reference asserts at lib/lib.rs:89)."""
     if not (1 <= level <= 9):
         raise BanzaiError(_ffi.EINVAL, f"level {level}")
-    data = reader.read()
-    out = _ctx().encode_bytes(data, level)
-    writer.write(out)
-    if hasattr(writer, "flush"):
-        writer.flush()
-    return len(data)
+    return _ctx().encode_stream(reader, writer, level)
 
 
 def encode_file(in_path, out_path):

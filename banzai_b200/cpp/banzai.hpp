@@ -7,6 +7,7 @@
 // Errors: the reference returns io::Result and panics on level outside 1..=9 (lib/lib.rs:89).
 // Here I/O and device errors throw std::runtime_error, a bad level throws std::invalid_argument.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <fstream>
 #include <istream>
@@ -51,16 +52,47 @@ inline std::vector<uint8_t> encode_bytes(Context &ctx, const uint8_t *data, size
 }
 
 // banzai::encode(reader, BufWriter, level) -> usize   (lib/lib.rs:84)
+// Streams: the reader fills pinned windows in place while the previous window is on the GPU, and
+// finished stream bytes go to the writer as they appear (bnz_stream_*), so pipes and inputs
+// larger than memory work like they do with the reference's refill loop (lib/rle.rs:43-91).
 inline size_t encode(Context &ctx, std::istream &reader, std::ostream &writer, int level)
 {
     if (level < 1 || level > 9) throw std::invalid_argument("level must be in 1..=9");
-    std::vector<uint8_t> data((std::istreambuf_iterator<char>(reader)), std::istreambuf_iterator<char>());
-    if (reader.bad()) throw std::runtime_error("read error");
-    std::vector<uint8_t> out = encode_bytes(ctx, data.data(), data.size(), level);
-    writer.write(reinterpret_cast<const char *>(out.data()), (std::streamsize)out.size());
+    auto err = [&](int rc) {
+        return std::runtime_error(std::string(bnz_strerror(rc)) + ": " + bnz_last_error(ctx.get()));
+    };
+    auto sink = [](void *user, const uint8_t *data, size_t len) -> int {
+        std::ostream *w = static_cast<std::ostream *>(user);
+        w->write(reinterpret_cast<const char *>(data), (std::streamsize)len);
+        return w->good() ? 0 : 1;
+    };
+    bnz_stream *s = nullptr;
+    int rc = bnz_stream_open(ctx.get(), level, sink, &writer, &s);
+    if (rc != BNZ_OK) throw err(rc);
+    struct Closer {
+        bnz_stream *s;
+        ~Closer() { bnz_stream_close(s); }
+    } closer{ s };
+    for (;;) {
+        uint8_t *buf = nullptr;
+        size_t cap = 0;
+        rc = bnz_stream_reserve(s, &buf, &cap);
+        if (rc != BNZ_OK) throw err(rc);
+        reader.read(reinterpret_cast<char *>(buf), (std::streamsize)std::min<size_t>(cap, (size_t)8 << 20));
+        const size_t got = (size_t)reader.gcount();
+        if (reader.bad()) throw std::runtime_error("read error");
+        if (got) {
+            rc = bnz_stream_commit(s, got);
+            if (rc != BNZ_OK) throw err(rc);
+        }
+        if (reader.eof() || got == 0) break;
+    }
+    size_t consumed = 0;
+    rc = bnz_stream_finish(s, &consumed);
+    if (rc != BNZ_OK) throw err(rc);
     writer.flush();                                     // out.rs:22-28 close() flushes
     if (!writer) throw std::runtime_error("write error");
-    return data.size();
+    return consumed;
 }
 
 // banzai::encode_file(in_path, out_path) -> usize, level 9   (lib/lib.rs:141-153)

@@ -39,7 +39,13 @@ namespace bwt {
 #endif
 constexpr int T = BWT_T;             // threads per CTA
 constexpr int NW = T / 32;           // warps per CTA
-constexpr int K = 8;                 // records per thread per tile
+#ifndef BWT_K
+#define BWT_K 8
+#endif
+#ifndef BWT_MINCTA
+#define BWT_MINCTA (1024 / BWT_T)
+#endif
+constexpr int K = BWT_K;             // records per thread per tile
 constexpr int TILE = T * K;          // 4096 records = 32 KB
 constexpr int KEY_BITS = 40;
 constexpr int IDX_BITS = 20;
@@ -561,7 +567,7 @@ __device__ void finalize_ties(Smem<BITS> &sm, const u64 *src, u32 count,
 }
 
 template <int BITS>
-__global__ void __launch_bounds__(T, 1024 / T) bwt_sort_kernel(BwtArgs a)
+__global__ void __launch_bounds__(T, BWT_MINCTA) bwt_sort_kernel(BwtArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<BITS> &sm = *reinterpret_cast<Smem<BITS> *>(smem_raw);

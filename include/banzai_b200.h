@@ -31,7 +31,8 @@ enum {
     BNZ_EINVAL = 1,     /* bad argument; level outside 1..=9 (the reference panics: lib/lib.rs:19,89) */
     BNZ_ECUDA = 2,      /* CUDA runtime / driver error, or no usable device */
     BNZ_ENOMEM = 3,     /* host or device allocation failed */
-    BNZ_EINTERNAL = 4   /* internal invariant violated (reference: assert!/panic! sites) */
+    BNZ_EINTERNAL = 4,  /* internal invariant violated (reference: assert!/panic! sites) */
+    BNZ_EIO = 5         /* a sink callback or a file operation failed (reference: io::Error via `?`) */
 };
 
 /* ---- context -------------------------------------------------------------------------
@@ -52,7 +53,7 @@ BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
  * per block), "bwt_cluster_below" (auto threshold in blocks), "bwt_threads" (512|1024, cluster
  * kernel), "bwt_radix_bits" (8|10, one-CTA kernel), "bwt_ctas_per_sm" (0 = auto),
  * "max_batch_bytes" (inputs above this, default 3 GiB, are encoded in streaming batches so that
- * device memory stays bounded; the stream bytes do not depend on it) */
+ * device memory stays bounded; the stream bytes do not depend on it), "stream_window_bytes" */
 BNZ_API int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value);
 
 /* ---- the hot path --------------------------------------------------------------------
@@ -79,9 +80,35 @@ BNZ_API int bnz_encode_device(bnz_ctx *ctx, const void *d_in, const uint8_t *h_i
 BNZ_API size_t bnz_max_compressed_size(size_t in_len);
 
 /* `banzai::encode_file(in_path, out_path)` (lib/lib.rs:141-153): level 9, returns bytes
- * encoded through *consumed. */
+ * encoded through *consumed.  Streams the file through bnz_stream_* (bounded memory). */
 BNZ_API int bnz_encode_file(bnz_ctx *ctx, const char *in_path, const char *out_path,
                             size_t *consumed);
+
+/* ---- streaming front end ---------------------------------------------------------------
+ * The reader/writer shape of `banzai::encode` (lib/lib.rs:84-132; refill loop
+ * lib/rle.rs:43-91; OutputStream lib/out.rs:7-104) for pipes and inputs larger than host
+ * or device memory.  The caller fills pinned windows in place (reserve -> read into *buf ->
+ * commit); while a full window is on the GPU the caller keeps reading the next one.  Finished
+ * stream bytes are handed to `sink` in order, always on the caller's thread and only inside
+ * bnz_stream_commit / _write / _finish.  The bytes written are exactly those of one bnz_encode
+ * over the concatenated input, whatever the commit sizes and the window size
+ * (bnz_ctx_set "stream_window_bytes", default 512 MiB; at least one block's worth is enforced).
+ * One open stream per context; the context must not be used otherwise until bnz_stream_close.
+ *   sink      : returns 0 on success; anything else aborts the stream with BNZ_EIO
+ *   reserve   : (*buf, *cap) = writable space for the next input bytes (cap >= 1)
+ *   commit    : n <= cap bytes were placed at *buf
+ *   write     : reserve + memcpy + commit for callers that already hold the bytes
+ *   finish    : encodes what is left, writes the footer (lib/lib.rs:66-70) and the zero padding
+ *               (lib/out.rs:22-28); *consumed = total input bytes (lib/lib.rs:131)
+ *   close     : releases the stream (also valid without finish: abandons the output) */
+typedef struct bnz_stream bnz_stream;
+typedef int (*bnz_sink_fn)(void *user, const uint8_t *data, size_t len);
+BNZ_API int bnz_stream_open(bnz_ctx *ctx, int level, bnz_sink_fn sink, void *user, bnz_stream **out);
+BNZ_API int bnz_stream_reserve(bnz_stream *s, uint8_t **buf, size_t *cap);
+BNZ_API int bnz_stream_commit(bnz_stream *s, size_t n);
+BNZ_API int bnz_stream_write(bnz_stream *s, const uint8_t *data, size_t len);
+BNZ_API int bnz_stream_finish(bnz_stream *s, size_t *consumed);
+BNZ_API void bnz_stream_close(bnz_stream *s);
 
 /* pinned host buffers for inputs (H2D at full PCIe rate) */
 BNZ_API void *bnz_host_alloc(size_t bytes);
