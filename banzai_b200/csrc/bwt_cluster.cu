@@ -150,7 +150,7 @@ __device__ u32 build_initial(Smem<T> &sm, const u8 *__restrict__ S, u32 n, u32 l
                 }
                 sm.present[(u32)(key >> 32)] = 1;
                 u64 rec = (key << IDX_BITS) | i;
-                seg[i - lo] = rec;
+                st_stream(seg + (i - lo), rec);
                 atomicAdd(&sm.nhist[c][digit_of(rec, 0)], 1u);
             }
         }
@@ -170,7 +170,7 @@ __device__ u32 build_round(Smem<T> &sm, const u32 *rank, u32 n, u32 h, u32 lo, u
 #pragma unroll
         for (int k = 0; k < K; k++) {
             u32 i = base + k * T + threadIdx.x;
-            r[k] = (i < hi) ? __ldcg(rank + i) : DONE;
+            r[k] = (i < hi) ? ld_keep_cg(rank + i) : DONE;
         }
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -179,7 +179,7 @@ __device__ u32 build_round(Smem<T> &sm, const u32 *rank, u32 n, u32 h, u32 lo, u
             if (!(r[k] & DONE)) {
                 u32 j = i + hm;
                 if (j >= n) j -= n;
-                r2[k] = __ldcg(rank + j);
+                r2[k] = ld_keep_cg(rank + j);
             }
         }
 #pragma unroll
@@ -193,7 +193,7 @@ __device__ u32 build_round(Smem<T> &sm, const u32 *rank, u32 n, u32 h, u32 lo, u
                 if (lane_id() == 0) wbase = atomicAdd(&sm.s_count, (u32)__popc(m));
                 wbase = __shfl_sync(0xffffffffu, wbase, 0);
                 if (act) {
-                    seg[wbase + __popc(m & lanemask_lt())] = rec;
+                    st_stream(seg + wbase + __popc(m & lanemask_lt()), rec);
                     atomicAdd(&sm.nhist[c][digit_of(rec, 0)], 1u);
                 }
             }
@@ -221,7 +221,7 @@ __device__ void radix_pass(Smem<T> &sm, const u64 *in, u32 in_cnt, u64 *dst, int
     if (tid == 0 && in_cnt > 0) {
         const u32 bytes = (min((u32)TILE, in_cnt) * 8u + 15u) & ~15u;
         mbar_expect_tx(&sm.mbar, bytes);
-        tma_load_1d(sm.inbuf, in, bytes, &sm.mbar);
+        tma_load_1d_stream(sm.inbuf, in, bytes, &sm.mbar);
     }
 
     // cursors: bucket start (all chunks) + records of the same digit in earlier chunks
@@ -275,7 +275,7 @@ __device__ void radix_pass(Smem<T> &sm, const u64 *in, u32 in_cnt, u64 *dst, int
             const u32 nb = (min((u32)TILE, in_cnt - base - TILE) * 8u + 15u) & ~15u;
             fence_proxy_async();
             mbar_expect_tx(&sm.mbar, nb);
-            tma_load_1d(sm.inbuf, in + base + TILE, nb, &sm.mbar);
+            tma_load_1d_stream(sm.inbuf, in + base + TILE, nb, &sm.mbar);
         }
 
         if (tid < BINS) {
@@ -314,7 +314,7 @@ __device__ void radix_pass(Smem<T> &sm, const u64 *in, u32 in_cnt, u64 *dst, int
                 const u64 r = sm.stage[j];
                 const u32 d = digit_of(r, pass);
                 const u32 q = sm.gbase[d] + j;
-                dst[q] = r;
+                st_stream(dst + q, r);
                 if (count_next) atomicAdd(&sm.nhist[och.chunk_of(q)][digit_of(r, pass + 1)], 1u);
             }
         }
@@ -440,11 +440,11 @@ __device__ RerankOut rerank(Smem<T> &sm, const u64 *src, u32 lo, u32 hi, u32 cou
             if (flg[k] & 1u) {
                 const u32 id = idx[k];
                 if (flg[k] & 2u) {
-                    rank[id] = nrv[k] | DONE;
+                    st_keep(rank + id, nrv[k] | DONE);
                     bwt_out[nrv[k]] = (u8)sb[k];
                     if (id == 0) *ptr_out = nrv[k];
                 } else if (!(flg[k] & 4u)) {
-                    rank[id] = nrv[k];
+                    st_keep(rank + id, nrv[k]);
                 }
             }
         }

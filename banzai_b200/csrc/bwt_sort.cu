@@ -131,7 +131,7 @@ __device__ void build_initial(Smem<BITS> &sm, const u8 *__restrict__ S, u32 n, u
                 }
                 sm.present[(u32)(key >> 32)] = 1;        // first byte = S[i]
                 u64 rec = (key << IDX_BITS) | i;
-                dst[i] = rec;
+                st_stream(dst + i, rec);
                 hist_add(sm, rec);
             }
         }
@@ -155,7 +155,7 @@ __device__ void build_round(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h,
 #pragma unroll
         for (int k = 0; k < K; k++) {
             u32 i = base + k * T + threadIdx.x;
-            r[k] = (i < n) ? rank[i] : DONE;
+            r[k] = (i < n) ? ld_keep(rank + i) : DONE;
         }
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -164,7 +164,7 @@ __device__ void build_round(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h,
             if (!(r[k] & DONE)) {
                 u32 j = i + hm;
                 if (j >= n) j -= n;
-                r2[k] = rank[j];
+                r2[k] = ld_keep(rank + j);
             }
         }
 #pragma unroll
@@ -178,7 +178,7 @@ __device__ void build_round(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h,
                 if (lane_id() == 0) wbase = atomicAdd(&sm.s_count, (u32)__popc(m));
                 wbase = __shfl_sync(0xffffffffu, wbase, 0);
                 if (act) {
-                    dst[wbase + __popc(m & lanemask_lt())] = rec;
+                    st_stream(dst + wbase + __popc(m & lanemask_lt()), rec);
                     hist_add(sm, rec);
                 }
             }
@@ -234,7 +234,7 @@ __device__ void build_round_list(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h, 
             if (j < cnt) {
                 u32 q = ((u32)e[k] & IDX_MASK) + hm;
                 if (q >= n) q -= n;
-                r2[k] = rank[q] & RANK_MASK;
+                r2[k] = ld_keep(rank + q) & RANK_MASK;
             }
         }
 #pragma unroll
@@ -244,7 +244,7 @@ __device__ void build_round_list(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h, 
                 const u32 idx = (u32)e[k] & IDX_MASK;
                 const u64 r1 = e[k] >> IDX_BITS;
                 const u64 rec = (r1 << (IDX_BITS + 20)) | ((u64)r2[k] << IDX_BITS) | idx;
-                dst[j] = rec;
+                st_stream(dst + j, rec);
                 hist_add(sm, rec);
             }
         }
@@ -271,7 +271,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
     if (tid == 0) {
         const u32 bytes = (min((u32)TILE, count) * 8u + 15u) & ~15u;
         mbar_expect_tx(&sm.mbar, bytes);
-        tma_load_1d(sm.inbuf, src, bytes, &sm.mbar);
+        tma_load_1d_stream(sm.inbuf, src, bytes, &sm.mbar);
     }
 
     // cursor = exclusive scan of this pass's histogram
@@ -334,7 +334,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             const u32 nb = (min((u32)TILE, count - base - TILE) * 8u + 15u) & ~15u;
             fence_proxy_async();
             mbar_expect_tx(&sm.mbar, nb);
-            tma_load_1d(sm.inbuf, src + base + TILE, nb, &sm.mbar);
+            tma_load_1d_stream(sm.inbuf, src + base + TILE, nb, &sm.mbar);
         }
 
         // cross-warp exclusive scan per bin, then exclusive scan over bins (NSCAN threads)
@@ -384,7 +384,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             for (int k = 0; k < K; k++) {
                 const u32 j = k * T + tid;
                 const u64 r = sm.stage[j];
-                dst[sm.gbase[digit_of<BITS>(r, pass)] + j] = r;
+                st_stream(dst + sm.gbase[digit_of<BITS>(r, pass)] + j, r);
             }
         } else {
 #pragma unroll
@@ -392,7 +392,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
                 const u32 j = k * T + tid;
                 if (j < tile_n) {
                     const u64 r = sm.stage[j];
-                    dst[sm.gbase[digit_of<BITS>(r, pass)] + j] = r;
+                    st_stream(dst + sm.gbase[digit_of<BITS>(r, pass)] + j, r);
                 }
             }
         }
@@ -501,11 +501,11 @@ __device__ RerankOut rerank(Smem<BITS> &sm, const u64 *src, u32 count, bool init
             if (flg[k] & 1u) {
                 const u32 id = idx[k];
                 if (flg[k] & 2u) {
-                    rank[id] = nrv[k] | DONE;
+                    st_keep(rank + id, nrv[k] | DONE);
                     bwt_out[nrv[k]] = (u8)sb[k];
                     if (id == 0) *ptr_out = nrv[k];
                 } else if (!(flg[k] & 4u)) {
-                    rank[id] = nrv[k];
+                    st_keep(rank + id, nrv[k]);
                 }
             }
         }

@@ -168,6 +168,60 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, u3
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 eviction-priority hints (the policy words createpolicy.fractional.L2::evict_* 1.0 produces).
+// Sort records stream through HBM once per pass: evict_first keeps them from flushing the
+// randomly accessed rank[] / S arrays out of the 126 MB L2.
+#ifndef BWT_L2HINT
+#define BWT_L2HINT 2
+#endif
+constexpr u64 L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_1d_stream(void *smem_dst, const void *gsrc, u32 bytes, u64 *bar)
+{
+#if BWT_L2HINT >= 1
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(L2_EVICT_FIRST)
+                 : "memory");
+#else
+    tma_load_1d(smem_dst, gsrc, bytes, bar);
+#endif
+}
+__device__ __forceinline__ void st_stream(u64 *p, u64 v)
+{
+#if BWT_L2HINT >= 1
+    asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(L2_EVICT_FIRST) : "memory");
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ u32 ld_keep(const u32 *p)
+{
+#if BWT_L2HINT >= 2
+    u32 v;
+    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(L2_EVICT_LAST) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ u32 ld_keep_cg(const u32 *p)      // L1 bypass (data written by other CTAs)
+{
+#if BWT_L2HINT >= 2
+    u32 v;
+    asm volatile("ld.global.cg.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(L2_EVICT_LAST) : "memory");
+    return v;
+#else
+    return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ void st_keep(u32 *p, u32 v)
+{
+#if BWT_L2HINT >= 2
+    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(L2_EVICT_LAST) : "memory");
+#else
+    *p = v;
+#endif
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 template <int NT>
