@@ -675,6 +675,12 @@ __global__ void __launch_bounds__(T, BWT_MINCTA) bwt_sort_kernel(BwtArgs a)
             a.stats[blk] = st;
         }
         __syncthreads();
+        if (a.done && tid == 0) {
+            // every thread's stores of this block precede the barrier; publish them, then raise the
+            // block's flag (host-mapped memory: the host launches the follow-up work of finished blocks)
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.done + blk), "r"(1u) : "memory");
+        }
     }
 }
 

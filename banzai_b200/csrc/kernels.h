@@ -68,6 +68,7 @@ struct BwtArgs {
     size_t ws_stride;             // >= max block length (+ cluster slack), multiple of 16
     void *ws_ctl;                 // cluster kernel only: per cluster BWT_CTL_BYTES of control state
     const uint32_t *order;        // optional: queue position -> block id (longest-first schedule)
+    uint32_t *done;               // optional [n_blocks], host-mapped: set to 1 (release.sys) when a block's outputs are complete
 };
 
 // cheap per-block cost predictor for the work queue: counts content-sampled 24-byte windows that
@@ -94,7 +95,8 @@ struct MtfArgs {
     const uint8_t *has_byte;      // [n_blocks][256]
     uint32_t n_blocks;
     const uint32_t *seg_base;     // [n_blocks + 1] first global segment of each block
-    uint32_t total_segs;
+    uint32_t seg0;                // first global segment of this range (= seg_base[0])
+    uint32_t total_segs;          // segments in this range
     uint8_t *seg_list;            // [total_segs][256] distinct bytes, newest first
     uint32_t *seg_cnt;            // [total_segs]
     uint8_t *seg_state;           // [total_segs][256] recency list at the segment start

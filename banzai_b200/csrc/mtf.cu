@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(NT1) mtf_summary_kernel(MtfArgs a)
 {
     __shared__ u32 seen[8][NT1];      // seen[k][tid]: conflict-free per-thread 256-bit set
     const u32 tid = threadIdx.x;
-    const u32 seg = blockIdx.x * NT1 + tid;
-    if (seg >= a.total_segs) return;
+    const u32 seg = a.seg0 + blockIdx.x * NT1 + tid;
+    if (seg >= a.seg0 + a.total_segs) return;
     const u32 b = find_block(a.seg_base, a.n_blocks, seg);
     const u32 s = seg - a.seg_base[b];
     const u32 n = a.blk_len[b];
@@ -148,11 +148,12 @@ __global__ void __launch_bounds__(NT1) mtf_apply_kernel(MtfArgs a)
 {
     extern __shared__ __align__(16) u8 rows[];          // NT1 rows of ROW bytes
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
-    const u32 seg0 = blockIdx.x * NT1;
+    const u32 seg0 = a.seg0 + blockIdx.x * NT1;
+    const u32 seg_end = a.seg0 + a.total_segs;
     // cooperative, coalesced load of the 32 starting lists of this warp
     for (u32 t = 0; t < 32; t++) {
         u32 sg = seg0 + w * 32 + t;
-        if (sg < a.total_segs) {
+        if (sg < seg_end) {
             uint2 v = *reinterpret_cast<const uint2 *>(a.seg_state + (size_t)sg * 256 + lane * 8);
             u8 *row = rows + (w * 32 + t) * ROW;
             *reinterpret_cast<u32 *>(row + lane * 8) = v.x;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(NT1) mtf_apply_kernel(MtfArgs a)
     }
     __syncwarp();
     const u32 seg = seg0 + tid;
-    if (seg >= a.total_segs) return;
+    if (seg >= seg_end) return;
     const u32 b = find_block(a.seg_base, a.n_blocks, seg);
     const u32 s = seg - a.seg_base[b];
     const u32 n = a.blk_len[b];

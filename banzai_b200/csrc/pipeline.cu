@@ -58,7 +58,7 @@ struct PinBuf {                      // grow-only pinned host staging
         p = nullptr;
         cap = 0;
         size_t want = bytes + bytes / 4 + 4096;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped);
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -76,14 +76,15 @@ struct Device {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;     // side stream: block CRCs run beside the sort
+    cudaStream_t stream3 = nullptr;     // low-priority stream: MTF of finished blocks fills the sort's tail
     // arenas (grown on demand, kept across calls)
     DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, bwt_score, bwt_order;
     DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, rle_blocks, crc_acc;
     DevBuf seg_base, seg_list, seg_cnt, seg_state, num_names, syms, sym_off, sym_len, freqs;
     DevBuf lens, codes, tf, num_tables, num_sel, span_base, hdr, hdr_bits, crc, blk_bits, blk_bitoff,
         total_bits, out;
-    cudaEvent_t ev[12] = {};
-    PinBuf h_P, h_oin, h_acc;
+    cudaEvent_t ev[14] = {};
+    PinBuf h_P, h_oin, h_acc, h_done;   // h_done: per-block completion flags the sort writes (mapped)
     bool crc_tables = false;
     uint32_t launches = 0;
 };
@@ -107,6 +108,8 @@ struct bnz_ctx {
     size_t max_batch_bytes = (size_t)3 << 30;   // inputs above this are encoded in streaming batches
     size_t stream_window_bytes = (size_t)512 << 20;   // bnz_stream_*: input bytes per pipeline window
     int open_streams = 0;
+    int mtf_groups = 1;
+    int mtf_overlap = 70;              // percent of a device's blocks whose MTF may run beside the sort (0: off)
 };
 
 // worker threads of a multi-device encode record their error text in their own string
@@ -166,10 +169,14 @@ extern "C" int bnz_ctx_create_on(bnz_ctx **out, const int *device_ids, int n_dev
         Device &d = ctx->devs.back();
         d.id = device_ids[i];
         cudaDeviceProp prop;
+        int prio_lo = 0, prio_hi = 0;
         bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaGetDeviceProperties(&prop, d.id) == cudaSuccess &&
                   prop.major >= 10 &&        // kernels are built for sm_100a only; fail loudly
-                  cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking) == cudaSuccess;
+                  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess &&
+                  // the sort's persistent CTAs must win every SM slot over the work that fills its tail
+                  cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&d.stream2, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&d.stream3, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
         for (cudaEvent_t &e : d.ev)
             if (ok && cudaEventCreate(&e) != cudaSuccess) ok = false;
         if (!ok) {
@@ -212,8 +219,10 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
         d.h_P.release();
         d.h_oin.release();
         d.h_acc.release();
+        d.h_done.release();
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.stream2) cudaStreamDestroy(d.stream2);
+        if (d.stream3) cudaStreamDestroy(d.stream3);
     }
     if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
     free(ctx->out_big);
@@ -236,6 +245,16 @@ extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
     if (!strcmp(key, "max_batch_bytes")) {
         if (value < (1 << 20)) return BNZ_EINVAL;
         ctx->max_batch_bytes = (size_t)value;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "mtf_groups")) {
+        if (value < 1 || value > 16) return BNZ_EINVAL;
+        ctx->mtf_groups = (int)value;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "mtf_overlap")) {
+        if (value < 0 || value > 95) return BNZ_EINVAL;
+        ctx->mtf_overlap = (int)value;
         return BNZ_OK;
     }
     if (!strcmp(key, "stream_window_bytes")) {
@@ -328,8 +347,10 @@ extern "C" size_t bnz_max_compressed_size(size_t in_len)
 
 static int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt,
                           const uint64_t *d_blk_off, const uint32_t *d_blk_len, uint32_t n_blocks,
-                          uint32_t max_len, uint32_t *d_ptr, uint8_t *d_has_byte, BwtStats *d_stats)
+                          uint32_t max_len, uint32_t *d_ptr, uint8_t *d_has_byte, BwtStats *d_stats,
+                          uint32_t *d_done = nullptr, bool *done_armed = nullptr)
 {
+    if (done_armed) *done_armed = false;
     if (n_blocks == 0) return BNZ_OK;
     CK(ctx, d.counters.ensure(256));
     CK(ctx, cudaMemsetAsync(d.counters.p, 0, 256, d.stream));
@@ -345,6 +366,7 @@ static int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t
     a.n_blocks = n_blocks;
     a.ws_ctl = nullptr;
     a.order = nullptr;
+    a.done = nullptr;
 
     // auto: many blocks -> one persistent CTA per block (best aggregate throughput);
     // few blocks -> one cluster per block so that every SM has work and the randomly accessed
@@ -413,6 +435,10 @@ static int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t
     a.ws_rec = d.ws_rec.as<uint64_t>();
     a.ws_rank = d.ws_rank.as<uint32_t>();
     a.ws_stride = stride;
+    if (d_done && n_blocks > (uint32_t)grid) {          // per-block completion flags (the queue has a tail)
+        a.done = d_done;
+        if (done_armed) *done_armed = true;
+    }
     CK(ctx, bwt_launch(a, ctx->radix_bits, grid, d.stream));
     d.launches++;
     return BNZ_OK;
@@ -686,8 +712,7 @@ static int upload_batch(bnz_ctx *ctx, Device &d, const Batch &bt)
 
 // bwt bytes in d_bwt -> symbols in d.syms (+ sym_len, num_names, freqs); d_idx is scratch of
 // the same size/layout as d_bwt.
-static int run_mtf_device(bnz_ctx *ctx, Device &d, const Batch &bt, const uint8_t *d_bwt, uint8_t *d_idx,
-                          const uint8_t *d_has_byte)
+static int mtf_ensure(bnz_ctx *ctx, Device &d, const Batch &bt)
 {
     const uint32_t nb = (uint32_t)bt.blk_len.size();
     const uint32_t segs = bt.seg_base[nb];
@@ -698,25 +723,42 @@ static int run_mtf_device(bnz_ctx *ctx, Device &d, const Batch &bt, const uint8_
     CK(ctx, d.syms.ensure(bt.syms_total * 2));
     CK(ctx, d.sym_len.ensure((size_t)nb * 4));
     CK(ctx, d.freqs.ensure((size_t)nb * 258 * 4));
+    return BNZ_OK;
+}
+
+// blocks [b0, b1) of the batch on stream `st`
+static int run_mtf_range(bnz_ctx *ctx, Device &d, const Batch &bt, const uint8_t *d_bwt, uint8_t *d_idx,
+                         const uint8_t *d_has_byte, uint32_t b0, uint32_t b1, cudaStream_t st)
+{
+    if (b1 <= b0) return BNZ_OK;
     MtfArgs a;
     a.bwt = d_bwt;
     a.idx = d_idx;
-    a.blk_off = d.blk_off.as<uint64_t>();
-    a.blk_len = d.blk_len.as<uint32_t>();
-    a.has_byte = d_has_byte;
-    a.n_blocks = nb;
-    a.seg_base = d.seg_base.as<uint32_t>();
-    a.total_segs = segs;
+    a.blk_off = d.blk_off.as<uint64_t>() + b0;
+    a.blk_len = d.blk_len.as<uint32_t>() + b0;
+    a.has_byte = d_has_byte + (size_t)b0 * 256;
+    a.n_blocks = b1 - b0;
+    a.seg_base = d.seg_base.as<uint32_t>() + b0;
+    a.seg0 = bt.seg_base[b0];
+    a.total_segs = bt.seg_base[b1] - bt.seg_base[b0];
     a.seg_list = d.seg_list.as<uint8_t>();
     a.seg_cnt = d.seg_cnt.as<uint32_t>();
     a.seg_state = d.seg_state.as<uint8_t>();
-    a.num_names = d.num_names.as<uint32_t>();
+    a.num_names = d.num_names.as<uint32_t>() + b0;
     a.syms = d.syms.as<uint16_t>();
-    a.sym_off = d.sym_off.as<uint64_t>();
-    a.sym_len = d.sym_len.as<uint32_t>();
-    a.freqs = d.freqs.as<uint32_t>();
-    CK(ctx, mtf_launch(a, d.stream, &d.launches));
+    a.sym_off = d.sym_off.as<uint64_t>() + b0;
+    a.sym_len = d.sym_len.as<uint32_t>() + b0;
+    a.freqs = d.freqs.as<uint32_t>() + (size_t)b0 * 258;
+    CK(ctx, mtf_launch(a, st, &d.launches));
     return BNZ_OK;
+}
+
+static int run_mtf_device(bnz_ctx *ctx, Device &d, const Batch &bt, const uint8_t *d_bwt, uint8_t *d_idx,
+                          const uint8_t *d_has_byte)
+{
+    int rc = mtf_ensure(ctx, d, bt);
+    if (rc != BNZ_OK) return rc;
+    return run_mtf_range(ctx, d, bt, d_bwt, d_idx, d_has_byte, 0, (uint32_t)bt.blk_len.size(), d.stream);
 }
 
 static size_t hdr_stride_words(int level)
@@ -953,9 +995,20 @@ static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t
         if (sh.bwt_after->bwt_recorded.load() > 0) CK(ctx, cudaStreamWaitEvent(d.stream, sh.bwt_after->d->ev[3], 0));
         CK(ctx, cudaEventRecord(d.ev[2], d.stream));       // RLE stage ends where the sort may start
     }
+    // MTF arenas and the completion flags are set up before the sort is launched (allocation
+    // would synchronise with it)
+    rc = mtf_ensure(ctx, d, bt);
+    if (rc != BNZ_OK) return rc;
+    CK(ctx, d.h_done.ensure((size_t)nb * 4));
+    volatile uint32_t *h_done = d.h_done.as<uint32_t>();
+    memset(d.h_done.p, 0, (size_t)nb * 4);
+    uint32_t *d_done = nullptr;
+    CK(ctx, cudaHostGetDevicePointer((void **)&d_done, d.h_done.p, 0));
+    CK(ctx, cudaEventRecord(d.ev[12], d.stream));
+    bool armed = false;
     rc = run_bwt_device(ctx, d, d.rle.as<uint8_t>(), d.bwt.as<uint8_t>(), d.blk_off.as<uint64_t>(),
                         d.blk_len.as<uint32_t>(), nb, bt.max_len, d.ptr.as<uint32_t>(), d.has_byte.as<uint8_t>(),
-                        d.bwt_stats.as<BwtStats>());
+                        d.bwt_stats.as<BwtStats>(), ctx->mtf_overlap > 0 ? d_done : nullptr, &armed);
     if (rc != BNZ_OK) {
         sh.bwt_recorded.store(-1, std::memory_order_release);
         return rc;
@@ -963,9 +1016,38 @@ static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t
     CK(ctx, cudaEventRecord(d.ev[3], d.stream));
     sh.bwt_recorded.store(1, std::memory_order_release);
 
-    // K5 (the RLE1 images are dead now: their buffer holds the MTF index bytes)
-    rc = run_mtf_device(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>());
+    // K5 (the RLE1 images are dead once their block is sorted: their buffer holds the MTF index
+    // bytes).  The one-CTA-per-block sort ends in a long tail (blocks differ 5x in cost and only
+    // ~4 fit per CTA), so the MTF of the blocks that finish first runs beside it: the sort raises a
+    // host-visible flag per finished block, and as soon as a leading group of blocks is complete
+    // this thread queues its MTF on a low-priority stream, whose CTAs get the SM slots the sort
+    // leaves empty.
+    uint32_t b_over = 0;
+    if (armed) {
+        CK(ctx, cudaStreamWaitEvent(d.stream3, d.ev[12], 0));
+        const uint32_t b_end = (uint32_t)((uint64_t)nb * (uint32_t)ctx->mtf_overlap / 100);
+        const uint32_t step = std::max<uint32_t>(32, b_end / (uint32_t)ctx->mtf_groups + 1);
+        uint32_t cur = 0;                      // blocks [0, cur) are sorted
+        while (b_over < b_end) {
+            const uint32_t g1 = std::min(b_end, b_over + step);
+            while (cur < g1 && h_done[cur]) cur++;
+            if (cur >= g1) {
+                std::atomic_thread_fence(std::memory_order_acquire);
+                rc = run_mtf_range(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>(), b_over,
+                                   g1, d.stream3);
+                if (rc != BNZ_OK) return rc;
+                b_over = g1;
+                continue;
+            }
+            if (cudaEventQuery(d.ev[3]) != cudaErrorNotReady) break;       // the sort ended (or failed)
+            std::this_thread::yield();
+        }
+        CK(ctx, cudaEventRecord(d.ev[13], d.stream3));
+    }
+    rc = run_mtf_range(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>(), b_over, nb,
+                       d.stream);
     if (rc != BNZ_OK) return rc;
+    if (armed) CK(ctx, cudaStreamWaitEvent(d.stream, d.ev[13], 0));
     CK(ctx, cudaEventRecord(d.ev[4], d.stream));
 
     // K6/K7 + headers + block bit lengths (the headers need the block CRCs from the side stream)

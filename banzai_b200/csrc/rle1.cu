@@ -644,7 +644,7 @@ int rle_walk_cuts(const uint8_t *in, uint64_t N, int level, const uint64_t *P, c
         if (bk.c <= bk.s || bk.n == 0 || bk.n > M) return -1;
         if (!final && bk.c >= N) break;          // ran out of data, not out of capacity
         blocks.push_back(bk);
-        rle_off += (bk.n + 15) & ~15ull;         // keep every block's RLE1 image 16-byte aligned
+        rle_off += (bk.n + 127) & ~127ull;       // every block's image starts on its own 128-byte line
         s = bk.c;
     }
     if (consumed) *consumed = blocks.empty() ? 0 : blocks.back().c;
