@@ -93,10 +93,11 @@ struct MtfArgs {
     const uint64_t *blk_off;      // [n_blocks]
     const uint32_t *blk_len;      // [n_blocks]
     const uint8_t *has_byte;      // [n_blocks][256]
-    uint32_t n_blocks;
-    const uint32_t *seg_base;     // [n_blocks + 1] first global segment of each block
-    uint32_t seg0;                // first global segment of this range (= seg_base[0])
-    uint32_t total_segs;          // segments in this range
+    uint32_t n_blocks;            // blocks handled by this launch (a list: any subset of the batch, any order)
+    const uint32_t *ids;          // [n_blocks] list position -> block id; every per-block array is indexed by block id
+    const uint32_t *cseg_base;    // [n_blocks + 1] running segment count over the list
+    const uint32_t *seg_base;     // [batch blocks + 1] first global segment of each block
+    uint32_t total_segs;          // segments in this launch (= cseg_base[n_blocks])
     uint8_t *seg_list;            // [total_segs][256] distinct bytes, newest first
     uint32_t *seg_cnt;            // [total_segs]
     uint8_t *seg_state;           // [total_segs][256] recency list at the segment start

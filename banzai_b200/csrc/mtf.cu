@@ -42,10 +42,12 @@ __global__ void __launch_bounds__(NT1) mtf_summary_kernel(MtfArgs a)
 {
     __shared__ u32 seen[8][NT1];      // seen[k][tid]: conflict-free per-thread 256-bit set
     const u32 tid = threadIdx.x;
-    const u32 seg = a.seg0 + blockIdx.x * NT1 + tid;
-    if (seg >= a.seg0 + a.total_segs) return;
-    const u32 b = find_block(a.seg_base, a.n_blocks, seg);
-    const u32 s = seg - a.seg_base[b];
+    const u32 segc = blockIdx.x * NT1 + tid;             // position in this launch's segment list
+    if (segc >= a.total_segs) return;
+    const u32 bc = find_block(a.cseg_base, a.n_blocks, segc);
+    const u32 s = segc - a.cseg_base[bc];
+    const u32 b = a.ids[bc];
+    const u32 seg = a.seg_base[b] + s;
     const u32 n = a.blk_len[b];
     const u8 *src = a.bwt + a.blk_off[b];
     const u32 start = s * SEG, end = min(start + SEG, n);
@@ -82,8 +84,9 @@ __global__ void __launch_bounds__(W2 * 32) mtf_compose_kernel(MtfArgs a)
     __shared__ __align__(8) u8 L[W2][2][256];
     __shared__ u32 mask[W2][8];
     const u32 w = warp_id(), lane = lane_id();
-    const u32 b = blockIdx.x * W2 + w;
-    if (b >= a.n_blocks) return;
+    const u32 bc = blockIdx.x * W2 + w;
+    if (bc >= a.n_blocks) return;
+    const u32 b = a.ids[bc];
     const u8 *has = a.has_byte + (size_t)b * 256;
 
     // initial list: present bytes ascending
@@ -148,12 +151,25 @@ __global__ void __launch_bounds__(NT1) mtf_apply_kernel(MtfArgs a)
 {
     extern __shared__ __align__(16) u8 rows[];          // NT1 rows of ROW bytes
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
-    const u32 seg0 = a.seg0 + blockIdx.x * NT1;
-    const u32 seg_end = a.seg0 + a.total_segs;
+    const u32 segc = blockIdx.x * NT1 + tid;             // position in this launch's segment list
+    const bool live = segc < a.total_segs;
+    u32 seg = 0, n = 0, start = 0;
+    const u8 *src = nullptr;
+    u8 *dst = nullptr;
+    if (live) {
+        const u32 bc = find_block(a.cseg_base, a.n_blocks, segc);
+        const u32 s = segc - a.cseg_base[bc];
+        const u32 b = a.ids[bc];
+        seg = a.seg_base[b] + s;
+        n = a.blk_len[b];
+        src = a.bwt + a.blk_off[b];
+        dst = a.idx + a.blk_off[b];
+        start = s * SEG;
+    }
     // cooperative, coalesced load of the 32 starting lists of this warp
     for (u32 t = 0; t < 32; t++) {
-        u32 sg = seg0 + w * 32 + t;
-        if (sg < seg_end) {
+        const u32 sg = __shfl_sync(0xffffffffu, seg, t);
+        if (__shfl_sync(0xffffffffu, (u32)live, t)) {
             uint2 v = *reinterpret_cast<const uint2 *>(a.seg_state + (size_t)sg * 256 + lane * 8);
             u8 *row = rows + (w * 32 + t) * ROW;
             *reinterpret_cast<u32 *>(row + lane * 8) = v.x;
@@ -161,14 +177,8 @@ __global__ void __launch_bounds__(NT1) mtf_apply_kernel(MtfArgs a)
         }
     }
     __syncwarp();
-    const u32 seg = seg0 + tid;
-    if (seg >= seg_end) return;
-    const u32 b = find_block(a.seg_base, a.n_blocks, seg);
-    const u32 s = seg - a.seg_base[b];
-    const u32 n = a.blk_len[b];
-    const u8 *src = a.bwt + a.blk_off[b];
-    u8 *dst = a.idx + a.blk_off[b];
-    const u32 start = s * SEG, end = min(start + SEG, n);
+    if (!live) return;
+    const u32 end = min(start + SEG, n);
     u8 *row = rows + tid * ROW;
     // list positions 0..7 live in a register (byte i = position i); 8..255 stay in the row
     u64 hq = 0;
@@ -245,7 +255,7 @@ __global__ void __launch_bounds__(T4) mtf_rle2_kernel(MtfArgs a)
     __shared__ u32 hist[260];
     __shared__ u32 scratch[40];
     const u32 tid = threadIdx.x;
-    const u32 b = blockIdx.x;
+    const u32 b = a.ids[blockIdx.x];
     const u32 n = a.blk_len[b];
     const u8 *idx = a.idx + a.blk_off[b];
     u16 *out = a.syms + a.sym_off[b];

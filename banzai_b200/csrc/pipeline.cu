@@ -76,15 +76,15 @@ struct Device {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;     // side stream: block CRCs run beside the sort
-    cudaStream_t stream3 = nullptr;     // low-priority stream: MTF of finished blocks fills the sort's tail
+    cudaStream_t stream3[3] = {};       // low-priority streams: MTF of finished blocks fills the sort's tail
     // arenas (grown on demand, kept across calls)
     DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, bwt_score, bwt_order;
     DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, rle_blocks, crc_acc;
-    DevBuf seg_base, seg_list, seg_cnt, seg_state, num_names, syms, sym_off, sym_len, freqs;
+    DevBuf seg_base, seg_list, seg_cnt, seg_state, num_names, syms, sym_off, sym_len, freqs, mtf_ids, mtf_cseg;
     DevBuf lens, codes, tf, num_tables, num_sel, span_base, hdr, hdr_bits, crc, blk_bits, blk_bitoff,
         total_bits, out;
-    cudaEvent_t ev[14] = {};
-    PinBuf h_P, h_oin, h_acc, h_done;   // h_done: per-block completion flags the sort writes (mapped)
+    cudaEvent_t ev[16] = {};
+    PinBuf h_P, h_oin, h_acc, h_mtf, h_done;   // h_done: per-block completion flags the sort writes (mapped)
     bool crc_tables = false;
     uint32_t launches = 0;
 };
@@ -108,7 +108,7 @@ struct bnz_ctx {
     size_t max_batch_bytes = (size_t)3 << 30;   // inputs above this are encoded in streaming batches
     size_t stream_window_bytes = (size_t)512 << 20;   // bnz_stream_*: input bytes per pipeline window
     int open_streams = 0;
-    int mtf_groups = 1;
+    int mtf_groups = 2;
     int mtf_overlap = 70;              // percent of a device's blocks whose MTF may run beside the sort (0: off)
 };
 
@@ -176,7 +176,9 @@ extern "C" int bnz_ctx_create_on(bnz_ctx **out, const int *device_ids, int n_dev
                   // the sort's persistent CTAs must win every SM slot over the work that fills its tail
                   cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
                   cudaStreamCreateWithPriority(&d.stream2, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
-                  cudaStreamCreateWithPriority(&d.stream3, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+                  cudaStreamCreateWithPriority(&d.stream3[0], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&d.stream3[1], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&d.stream3[2], cudaStreamNonBlocking, prio_lo) == cudaSuccess;
         for (cudaEvent_t &e : d.ev)
             if (ok && cudaEventCreate(&e) != cudaSuccess) ok = false;
         if (!ok) {
@@ -210,7 +212,7 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
                            &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.bwt_score, &d.bwt_order, &d.ch_lasthead, &d.ch_meta,
                            &d.ch_restsum, &d.ch_oin, &d.ch_P, &d.rle_blocks, &d.crc_acc, &d.seg_base,
                            &d.seg_list, &d.seg_cnt, &d.seg_state, &d.num_names, &d.syms, &d.sym_off,
-                           &d.sym_len, &d.freqs, &d.lens, &d.codes, &d.tf, &d.num_tables, &d.num_sel,
+                           &d.sym_len, &d.freqs, &d.mtf_ids, &d.mtf_cseg, &d.lens, &d.codes, &d.tf, &d.num_tables, &d.num_sel,
                            &d.span_base, &d.hdr, &d.hdr_bits, &d.crc, &d.blk_bits, &d.blk_bitoff,
                            &d.total_bits, &d.out })
             b->release();
@@ -220,9 +222,11 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
         d.h_oin.release();
         d.h_acc.release();
         d.h_done.release();
+        d.h_mtf.release();
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.stream2) cudaStreamDestroy(d.stream2);
-        if (d.stream3) cudaStreamDestroy(d.stream3);
+        for (cudaStream_t st : d.stream3)
+            if (st) cudaStreamDestroy(st);
     }
     if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
     free(ctx->out_big);
@@ -723,32 +727,56 @@ static int mtf_ensure(bnz_ctx *ctx, Device &d, const Batch &bt)
     CK(ctx, d.syms.ensure(bt.syms_total * 2));
     CK(ctx, d.sym_len.ensure((size_t)nb * 4));
     CK(ctx, d.freqs.ensure((size_t)nb * 258 * 4));
+    CK(ctx, d.mtf_ids.ensure((size_t)nb * 4));
+    CK(ctx, d.mtf_cseg.ensure(((size_t)nb + 64) * 4));
+    CK(ctx, d.h_mtf.ensure(((size_t)nb * 2 + 64) * 4));
     return BNZ_OK;
 }
 
-// blocks [b0, b1) of the batch on stream `st`
-static int run_mtf_range(bnz_ctx *ctx, Device &d, const Batch &bt, const uint8_t *d_bwt, uint8_t *d_idx,
-                         const uint8_t *d_has_byte, uint32_t b0, uint32_t b1, cudaStream_t st)
+// MTF of a list of blocks of the batch (any subset, any order) on stream `st`.  `ids_used` /
+// `lists_used` count what earlier lists of the same batch took from the id / segment-prefix
+// arrays (every block is listed once per batch, so nothing is overwritten while in use).
+static int run_mtf_list(bnz_ctx *ctx, Device &d, const Batch &bt, const uint8_t *d_bwt, uint8_t *d_idx,
+                        const uint8_t *d_has_byte, const uint32_t *ids, uint32_t n_list, uint32_t &ids_used,
+                        uint32_t &lists_used, cudaStream_t st)
 {
-    if (b1 <= b0) return BNZ_OK;
+    if (n_list == 0) return BNZ_OK;
+    const uint32_t nb = (uint32_t)bt.blk_len.size();
+    if (ids_used + n_list > nb || lists_used >= 64) return fail(ctx, BNZ_EINTERNAL, "MTF list bookkeeping");
+    uint32_t *h_ids = d.h_mtf.as<uint32_t>() + ids_used;
+    uint32_t *h_cseg = d.h_mtf.as<uint32_t>() + nb + ids_used + lists_used;
+    uint32_t segs = 0;
+    for (uint32_t k = 0; k < n_list; k++) {
+        h_ids[k] = ids[k];
+        h_cseg[k] = segs;
+        segs += bt.seg_base[ids[k] + 1] - bt.seg_base[ids[k]];
+    }
+    h_cseg[n_list] = segs;
+    uint32_t *d_ids = d.mtf_ids.as<uint32_t>() + ids_used;
+    uint32_t *d_cseg = d.mtf_cseg.as<uint32_t>() + ids_used + lists_used;
+    CK(ctx, cudaMemcpyAsync(d_ids, h_ids, (size_t)n_list * 4, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(d_cseg, h_cseg, ((size_t)n_list + 1) * 4, cudaMemcpyHostToDevice, st));
+    ids_used += n_list;
+    lists_used++;
     MtfArgs a;
     a.bwt = d_bwt;
     a.idx = d_idx;
-    a.blk_off = d.blk_off.as<uint64_t>() + b0;
-    a.blk_len = d.blk_len.as<uint32_t>() + b0;
-    a.has_byte = d_has_byte + (size_t)b0 * 256;
-    a.n_blocks = b1 - b0;
-    a.seg_base = d.seg_base.as<uint32_t>() + b0;
-    a.seg0 = bt.seg_base[b0];
-    a.total_segs = bt.seg_base[b1] - bt.seg_base[b0];
+    a.blk_off = d.blk_off.as<uint64_t>();
+    a.blk_len = d.blk_len.as<uint32_t>();
+    a.has_byte = d_has_byte;
+    a.n_blocks = n_list;
+    a.ids = d_ids;
+    a.cseg_base = d_cseg;
+    a.seg_base = d.seg_base.as<uint32_t>();
+    a.total_segs = segs;
     a.seg_list = d.seg_list.as<uint8_t>();
     a.seg_cnt = d.seg_cnt.as<uint32_t>();
     a.seg_state = d.seg_state.as<uint8_t>();
-    a.num_names = d.num_names.as<uint32_t>() + b0;
+    a.num_names = d.num_names.as<uint32_t>();
     a.syms = d.syms.as<uint16_t>();
-    a.sym_off = d.sym_off.as<uint64_t>() + b0;
-    a.sym_len = d.sym_len.as<uint32_t>() + b0;
-    a.freqs = d.freqs.as<uint32_t>() + (size_t)b0 * 258;
+    a.sym_off = d.sym_off.as<uint64_t>();
+    a.sym_len = d.sym_len.as<uint32_t>();
+    a.freqs = d.freqs.as<uint32_t>();
     CK(ctx, mtf_launch(a, st, &d.launches));
     return BNZ_OK;
 }
@@ -758,7 +786,10 @@ static int run_mtf_device(bnz_ctx *ctx, Device &d, const Batch &bt, const uint8_
 {
     int rc = mtf_ensure(ctx, d, bt);
     if (rc != BNZ_OK) return rc;
-    return run_mtf_range(ctx, d, bt, d_bwt, d_idx, d_has_byte, 0, (uint32_t)bt.blk_len.size(), d.stream);
+    std::vector<uint32_t> all(bt.blk_len.size());
+    for (uint32_t b = 0; b < all.size(); b++) all[b] = b;
+    uint32_t ids_used = 0, lists_used = 0;
+    return run_mtf_list(ctx, d, bt, d_bwt, d_idx, d_has_byte, all.data(), (uint32_t)all.size(), ids_used, lists_used, d.stream);
 }
 
 static size_t hdr_stride_words(int level)
@@ -1022,32 +1053,44 @@ static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t
     // host-visible flag per finished block, and as soon as a leading group of blocks is complete
     // this thread queues its MTF on a low-priority stream, whose CTAs get the SM slots the sort
     // leaves empty.
-    uint32_t b_over = 0;
+    std::vector<uint32_t> list;
+    std::vector<uint8_t> taken(nb, 0);
+    uint32_t ids_used = 0, lists_used = 0;
     if (armed) {
-        CK(ctx, cudaStreamWaitEvent(d.stream3, d.ev[12], 0));
-        const uint32_t b_end = (uint32_t)((uint64_t)nb * (uint32_t)ctx->mtf_overlap / 100);
-        const uint32_t step = std::max<uint32_t>(32, b_end / (uint32_t)ctx->mtf_groups + 1);
-        uint32_t cur = 0;                      // blocks [0, cur) are sorted
-        while (b_over < b_end) {
-            const uint32_t g1 = std::min(b_end, b_over + step);
-            while (cur < g1 && h_done[cur]) cur++;
-            if (cur >= g1) {
+        for (cudaStream_t st : d.stream3) CK(ctx, cudaStreamWaitEvent(st, d.ev[12], 0));
+        const uint32_t budget = (uint32_t)((uint64_t)nb * (uint32_t)ctx->mtf_overlap / 100);   // blocks that may go beside the sort
+        const uint32_t step = std::max<uint32_t>(32, budget / (uint32_t)ctx->mtf_groups);
+        uint32_t n_over = 0;
+        int g = 0;
+        list.reserve(nb);
+        while (n_over < budget) {
+            for (uint32_t b = 0; b < nb && list.size() < step; b++)
+                if (!taken[b] && h_done[b]) {
+                    taken[b] = 1;
+                    list.push_back(b);
+                }
+            if (list.size() >= step) {
                 std::atomic_thread_fence(std::memory_order_acquire);
-                rc = run_mtf_range(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>(), b_over,
-                                   g1, d.stream3);
+                rc = run_mtf_list(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>(), list.data(),
+                                  (uint32_t)list.size(), ids_used, lists_used, d.stream3[g++ % 3]);
                 if (rc != BNZ_OK) return rc;
-                b_over = g1;
+                n_over += (uint32_t)list.size();
+                list.clear();
                 continue;
             }
             if (cudaEventQuery(d.ev[3]) != cudaErrorNotReady) break;       // the sort ended (or failed)
             std::this_thread::yield();
         }
-        CK(ctx, cudaEventRecord(d.ev[13], d.stream3));
+        for (int k = 0; k < 3; k++) CK(ctx, cudaEventRecord(d.ev[13 + k], d.stream3[k]));
     }
-    rc = run_mtf_range(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>(), b_over, nb,
-                       d.stream);
+    // everything not queued beside the sort follows it on the main stream
+    for (uint32_t b = 0; b < nb; b++)
+        if (!taken[b]) list.push_back(b);      // (a partly gathered list is already in `list`)
+    rc = run_mtf_list(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>(), list.data(),
+                      (uint32_t)list.size(), ids_used, lists_used, d.stream);
     if (rc != BNZ_OK) return rc;
-    if (armed) CK(ctx, cudaStreamWaitEvent(d.stream, d.ev[13], 0));
+    if (armed)
+        for (int k = 0; k < 3; k++) CK(ctx, cudaStreamWaitEvent(d.stream, d.ev[13 + k], 0));
     CK(ctx, cudaEventRecord(d.ev[4], d.stream));
 
     // K6/K7 + headers + block bit lengths (the headers need the block CRCs from the side stream)
