@@ -108,6 +108,7 @@ struct bnz_ctx {
     size_t max_batch_bytes = (size_t)3 << 30;   // inputs above this are encoded in streaming batches
     size_t stream_window_bytes = (size_t)512 << 20;   // bnz_stream_*: input bytes per pipeline window
     int open_streams = 0;
+    int crc_low_prio = 1;              // block CRCs on the low-priority stream (they would delay the start of the sort)
     int mtf_groups = 2;
     int mtf_overlap = 70;              // percent of a device's blocks whose MTF may run beside the sort (0: off)
 };
@@ -249,6 +250,10 @@ extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
     if (!strcmp(key, "max_batch_bytes")) {
         if (value < (1 << 20)) return BNZ_EINVAL;
         ctx->max_batch_bytes = (size_t)value;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "crc_low_prio")) {
+        ctx->crc_low_prio = value != 0;
         return BNZ_OK;
     }
     if (!strcmp(key, "mtf_groups")) {
@@ -595,10 +600,11 @@ static int rle_emit_shard(bnz_ctx *ctx, Device &d, const uint8_t *in_base, uint6
     CK(ctx, rle_emit_launch(in_base, N, c_begin, c_end, oin_base, P_base, d.rle_blocks.as<RleBlock>(), (uint32_t)nb,
                             d.rle.as<uint8_t>(), d.stream));
     // K2 on the side stream; d.ev[10] marks d.crc complete
-    CK(ctx, cudaStreamWaitEvent(d.stream2, d.ev[9], 0));
+    cudaStream_t crc_st = ctx->crc_low_prio ? d.stream3[2] : d.stream2;
+    CK(ctx, cudaStreamWaitEvent(crc_st, d.ev[9], 0));
     CK(ctx, crc_launch(in_base, N, c_begin, c_end, d.rle_blocks.as<RleBlock>(), (uint32_t)nb, d.crc_acc.as<uint32_t>(),
-                       d.crc.as<uint32_t>(), d.stream2));
-    CK(ctx, cudaEventRecord(d.ev[10], d.stream2));
+                       d.crc.as<uint32_t>(), crc_st));
+    CK(ctx, cudaEventRecord(d.ev[10], crc_st));
     d.launches += 3;
     if (crcs) {
         CK(ctx, d.h_acc.ensure(nb * 4));
