@@ -273,7 +273,7 @@ __device__ void radix_pass(Smem<T> &sm, const u64 *in, u32 in_cnt, u64 *dst, int
 
         if (tid == 0 && base + TILE < in_cnt) {
             const u32 nb = (min((u32)TILE, in_cnt - base - TILE) * 8u + 15u) & ~15u;
-            fence_proxy_async();
+            // (no proxy fence: see bwt_sort.cu — the reads of inbuf completed before B1)
             mbar_expect_tx(&sm.mbar, nb);
             tma_load_1d_stream(sm.inbuf, in + base + TILE, nb, &sm.mbar);
         }
