@@ -64,21 +64,25 @@ struct Cfg {
 template <int BITS>
 struct __align__(128) Smem {
     u64 inbuf[TILE];                                      // TMA landing zone for the next tile
-    u64 stage[TILE];                                      // tile reorder buffer
-    u32 whist[NW][Cfg<BITS>::BINS];                       // per-warp digit counts / offsets
+    u64 stage[TILE];                                      // tile reorder buffer (digit histograms while keys are built)
+    u32 whist[NW][Cfg<BITS>::BINS / 2];                   // per-warp digit counts / offsets, two 16-bit bins per word
     u32 cursor[Cfg<BITS>::BINS];                          // running bucket cursors (global)
-    u32 binoff[Cfg<BITS>::BINS];                          // exclusive bin offsets inside the tile
     u32 gbase[Cfg<BITS>::BINS];                           // cursor - binoff
-    u32 hist[Cfg<BITS>::PASSES][Cfg<BITS>::BINS];         // per-pass digit histograms
+    u16 binoff[Cfg<BITS>::BINS];                          // exclusive bin offsets inside the tile
     u64 scratch64[40];
     u64 mbar;                                             // mbarrier of the TMA tile pipeline
     u32 scratch[40];
     u32 s_count;                                          // records appended by build_*
     u32 s_list;                                           // active-list length appended by rerank
     u32 s_block;                                          // claimed block id
-    u32 s_flags[8];
+    u32 s_flags[8];                                       // per pass: every record has the same digit
     u8 present[256];                                      // has_byte
 };
+static_assert(Cfg<10>::PASSES * Cfg<10>::BINS * 4 <= TILE * 8, "histograms must fit the reorder buffer");
+
+// per-pass digit histograms: built in the (then idle) reorder buffer, parked in global memory
+template <int BITS>
+__device__ __forceinline__ u32 *hist_of(Smem<BITS> &sm) { return reinterpret_cast<u32 *>(sm.stage); }
 
 template <int BITS>
 __device__ __forceinline__ u32 digit_of(u64 rec, int pass)
@@ -89,7 +93,8 @@ __device__ __forceinline__ u32 digit_of(u64 rec, int pass)
 template <int BITS>
 __device__ __forceinline__ void hist_clear(Smem<BITS> &sm)
 {
-    for (int i = threadIdx.x; i < Cfg<BITS>::PASSES * Cfg<BITS>::BINS; i += T) (&sm.hist[0][0])[i] = 0;
+    u32 *hist = hist_of(sm);
+    for (int i = threadIdx.x; i < Cfg<BITS>::PASSES * Cfg<BITS>::BINS; i += T) hist[i] = 0;
     if (threadIdx.x == 0) sm.s_count = 0;
     __syncthreads();
 }
@@ -97,8 +102,9 @@ __device__ __forceinline__ void hist_clear(Smem<BITS> &sm)
 template <int BITS>
 __device__ __forceinline__ void hist_add(Smem<BITS> &sm, u64 rec)
 {
+    u32 *hist = hist_of(sm);
 #pragma unroll
-    for (int p = 0; p < Cfg<BITS>::PASSES; p++) atomicAdd(&sm.hist[p][digit_of<BITS>(rec, p)], 1u);
+    for (int p = 0; p < Cfg<BITS>::PASSES; p++) atomicAdd(&hist[p * Cfg<BITS>::BINS + digit_of<BITS>(rec, p)], 1u);
 }
 
 // Round 0: key = the five bytes S[i..i+5) (cyclic), big-endian, so h = 5 afterwards.
@@ -254,15 +260,36 @@ __device__ void build_round_list(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h, 
     __syncthreads();
 }
 
+// After the keys of a round are built: park the per-pass histograms in global memory (the
+// reorder buffer they were built in is needed by the passes) and note the passes whose digit is
+// the same for every record.
+template <int BITS>
+__device__ void hist_park(Smem<BITS> &sm, u32 *ghist, u32 count)
+{
+    constexpr int BINS = Cfg<BITS>::BINS, PASSES = Cfg<BITS>::PASSES;
+    const u32 *hist = hist_of(sm);
+    if (threadIdx.x < 8) sm.s_flags[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < PASSES * BINS; i += T) {
+        const u32 v = hist[i];
+        ghist[i] = v;
+        if (v == count) sm.s_flags[i / BINS] = 1;
+    }
+    __syncthreads();
+}
+
 // One LSD pass over `count` records: src -> dst by digit `pass`.
 // Tiles are streamed through shared memory with TMA bulk copies (cp.async.bulk + mbarrier):
 // the copy of tile t+1 is in flight while tile t is ranked, reordered and stored.
 template <int BITS>
-__device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, int pass, u32 &phase)
+__device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, int pass, const u32 *ghist,
+                           u32 &phase)
 {
     constexpr int BINS = Cfg<BITS>::BINS;
     constexpr int BPT = Cfg<BITS>::BPT;
-    constexpr int NSCAN = BINS / BPT;               // threads that own bins in the scans
+    constexpr int WORDS = BINS / 2;                             // packed counter words per warp row
+    constexpr int NSCAN = WORDS < T ? WORDS : T;                // threads that own counter words in the scan
+    static_assert(WORDS <= T, "one counter word per scan thread");
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
 
     // records were written with generic-proxy stores; order them before the async-proxy reads
@@ -280,7 +307,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
 #pragma unroll
         for (int j = 0; j < BPT; j++) {
             u32 b = tid * BPT + j;
-            c[j] = (b < BINS) ? sm.hist[pass][b] : 0;
+            c[j] = (b < BINS) ? ghist[pass * BINS + b] : 0;
             sum += c[j];
         }
         u32 tot;
@@ -300,7 +327,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
         u32 rk[K];
         {   // zero this warp's counter row with 16-byte stores
             uint4 *row = reinterpret_cast<uint4 *>(sm.whist[w]);
-            for (int b = lane; b < BINS * 4 / 16; b += 32) row[b] = make_uint4(0, 0, 0, 0);
+            for (int b = lane; b < WORDS / 4; b += 32) row[b] = make_uint4(0, 0, 0, 0);
         }
         mbar_wait(&sm.mbar, phase);
         phase ^= 1u;
@@ -321,12 +348,14 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             const u32 d = digit_of<BITS>(rec[k], pass);
             const u32 peers = match_digit<BITS>(d);
             const u32 leader = 31 - __clz(peers);
+            const u32 sh = (d & 1u) * 16u;
             // one shared atomic per digit group; its return value is the group's base.  Atomics of
             // successive rows to the same counter execute in program order, so rows need no barrier.
+            // (a warp holds at most 256 records of a tile, so the 16-bit halves never carry)
             u32 bcount = 0;
-            if (lane == leader) bcount = atomicAdd(&sm.whist[w][d], (u32)__popc(peers));
+            if (lane == leader) bcount = atomicAdd(&sm.whist[w][d >> 1], (u32)__popc(peers) << sh);
             bcount = __shfl_sync(0xffffffffu, bcount, leader);
-            rk[k] = bcount + __popc(peers & lanemask_lt());
+            rk[k] = ((bcount >> sh) & 0xffffu) + __popc(peers & lanemask_lt());
         }
         __syncthreads();                                        // B1: inbuf consumed, whist complete
 
@@ -339,44 +368,38 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             tma_load_1d_stream(sm.inbuf, src + base + TILE, nb, &sm.mbar);
         }
 
-        // cross-warp exclusive scan per bin, then exclusive scan over bins (NSCAN threads)
+        // cross-warp exclusive scan per bin (two bins per packed word; a tile holds 4096 records, so
+        // the halves never carry), then exclusive scan over bins
         if (tid < NSCAN) {
-            u32 c[BPT], sum = 0;
+            u32 run = 0;
 #pragma unroll
-            for (int j = 0; j < BPT; j++) {
-                const u32 b = tid * BPT + j;
-                u32 run = 0;
-#pragma unroll
-                for (int ww = 0; ww < NW; ww++) {
-                    u32 v = sm.whist[ww][b];
-                    sm.whist[ww][b] = run;
-                    run += v;
-                }
-                c[j] = run;
-                sum += run;
+            for (int ww = 0; ww < NW; ww++) {
+                const u32 v = sm.whist[ww][tid];
+                sm.whist[ww][tid] = run;
+                run += v;
             }
+            const u32 lo = run & 0xffffu, hi = run >> 16, sum = lo + hi;
             const u32 inc = warp_incl_sum(sum);
             if (lane == 31) sm.scratch[w] = inc;
             asm volatile("bar.sync 1, %0;" ::"n"(NSCAN) : "memory");
             u32 woff = 0;
             for (u32 q = 0; q < w; q++) woff += sm.scratch[q];
-            u32 ex = woff + inc - sum;
-#pragma unroll
-            for (int j = 0; j < BPT; j++) {
-                const u32 b = tid * BPT + j;
-                const u32 cur = sm.cursor[b];
-                sm.binoff[b] = ex;
-                sm.gbase[b] = cur - ex;
-                sm.cursor[b] = cur + c[j];
-                ex += c[j];
-            }
+            const u32 ex = woff + inc - sum;
+            const u32 b0 = 2 * tid;
+            const u32 cur0 = sm.cursor[b0], cur1 = sm.cursor[b0 + 1];
+            sm.binoff[b0] = (u16)ex;
+            sm.binoff[b0 + 1] = (u16)(ex + lo);
+            sm.gbase[b0] = cur0 - ex;
+            sm.gbase[b0 + 1] = cur1 - (ex + lo);
+            sm.cursor[b0] = cur0 + lo;
+            sm.cursor[b0 + 1] = cur1 + hi;
         }
         __syncthreads();                                        // B2
 
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const u32 d = digit_of<BITS>(rec[k], pass);
-            const u32 pos = sm.binoff[d] + sm.whist[w][d] + rk[k];
+            const u32 pos = sm.binoff[d] + ((sm.whist[w][d >> 1] >> ((d & 1u) * 16u)) & 0xffffu) + rk[k];
             sm.stage[pos] = rec[k];
         }
         __syncthreads();                                        // B3
@@ -611,19 +634,13 @@ __global__ void __launch_bounds__(T, BWT_MINCTA) bwt_sort_kernel(BwtArgs a)
             t1 = clock64();
             cyc_build += t1 - t0;
 
+            u32 *ghist = a.ws_hist + (size_t)blockIdx.x * (PASSES * Cfg<BITS>::BINS);
+            hist_park<BITS>(sm, ghist, count);
             u64 *src = bufA, *dst = bufB;
             u32 passes_run = 0;
             for (int p = 0; p < PASSES; p++) {
-                // skip a pass whose digit is the same for every record
-                if (tid == 0) sm.s_flags[0] = 0;
-                __syncthreads();
-                for (int b = tid; b < Cfg<BITS>::BINS; b += T)
-                    if (sm.hist[p][b] == count) sm.s_flags[0] = 1;
-                __syncthreads();
-                const bool skip = sm.s_flags[0] != 0;
-                __syncthreads();
-                if (skip) continue;
-                radix_pass<BITS>(sm, src, dst, count, p, phase);
+                if (sm.s_flags[p]) continue;               // every record has the same digit: nothing moves
+                radix_pass<BITS>(sm, src, dst, count, p, ghist, phase);
                 u64 *t = src; src = dst; dst = t;
                 passes_run++;
             }

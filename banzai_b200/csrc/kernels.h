@@ -53,6 +53,7 @@ struct BwtStats {                 // per bzip2 block, written by the sort kernel
     uint64_t cyc_build, cyc_radix, cyc_rerank;   // SM cycles spent per phase (thread 0's clock64)
 };
 
+constexpr int BWT_HIST_WORDS = 5 * 1024;
 struct BwtArgs {
     const uint8_t *rle;           // RLE1 bytes of all blocks (block b at rle + blk_off[b])
     uint8_t *bwt;                 // BWT bytes, same layout
@@ -66,6 +67,7 @@ struct BwtArgs {
     uint64_t *ws_rec;             // per CTA: 2 * ws_stride records
     uint32_t *ws_rank;            // per CTA: ws_stride ranks
     size_t ws_stride;             // >= max block length (+ cluster slack), multiple of 16
+    uint32_t *ws_hist;            // one-CTA kernel: per CTA BWT_HIST_WORDS words (per-pass digit histograms)
     void *ws_ctl;                 // cluster kernel only: per cluster BWT_CTL_BYTES of control state
     const uint32_t *order;        // optional: queue position -> block id (longest-first schedule)
     uint32_t *done;               // optional [n_blocks], host-mapped: set to 1 (release.sys) when a block's outputs are complete

@@ -78,7 +78,7 @@ struct Device {
     cudaStream_t stream2 = nullptr;     // side stream: block CRCs run beside the sort
     cudaStream_t stream3[3] = {};       // low-priority streams: MTF of finished blocks fills the sort's tail
     // arenas (grown on demand, kept across calls)
-    DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, bwt_score, bwt_order;
+    DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, ws_hist, bwt_score, bwt_order;
     DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, rle_blocks, crc_acc;
     DevBuf seg_base, seg_list, seg_cnt, seg_state, num_names, syms, sym_off, sym_len, freqs, mtf_ids, mtf_cseg;
     DevBuf lens, codes, tf, num_tables, num_sel, span_base, hdr, hdr_bits, crc, blk_bits, blk_bitoff,
@@ -210,7 +210,7 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
         cudaSetDevice(d.id);
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (DevBuf *b : { &d.in, &d.rle, &d.bwt, &d.blk_off, &d.blk_len, &d.ptr, &d.has_byte,
-                           &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.bwt_score, &d.bwt_order, &d.ch_lasthead, &d.ch_meta,
+                           &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.ws_hist, &d.bwt_score, &d.bwt_order, &d.ch_lasthead, &d.ch_meta,
                            &d.ch_restsum, &d.ch_oin, &d.ch_P, &d.rle_blocks, &d.crc_acc, &d.seg_base,
                            &d.seg_list, &d.seg_cnt, &d.seg_state, &d.num_names, &d.syms, &d.sym_off,
                            &d.sym_len, &d.freqs, &d.mtf_ids, &d.mtf_cseg, &d.lens, &d.codes, &d.tf, &d.num_tables, &d.num_sel,
@@ -374,6 +374,7 @@ static int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t
     a.next_block = d.counters.as<uint32_t>();
     a.n_blocks = n_blocks;
     a.ws_ctl = nullptr;
+    a.ws_hist = nullptr;
     a.order = nullptr;
     a.done = nullptr;
 
@@ -441,6 +442,8 @@ static int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t
     size_t stride = ((size_t)max_len + 15) & ~(size_t)15;
     CK(ctx, d.ws_rec.ensure((size_t)grid * 2 * stride * sizeof(uint64_t)));
     CK(ctx, d.ws_rank.ensure((size_t)grid * stride * sizeof(uint32_t)));
+    CK(ctx, d.ws_hist.ensure((size_t)grid * BWT_HIST_WORDS * 4));
+    a.ws_hist = d.ws_hist.as<uint32_t>();
     a.ws_rec = d.ws_rec.as<uint64_t>();
     a.ws_rank = d.ws_rank.as<uint32_t>();
     a.ws_stride = stride;
