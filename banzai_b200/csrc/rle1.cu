@@ -24,6 +24,7 @@ namespace rle {
 constexpr int CH = RLE_CHUNK;        // 1024 bytes per chunk = 32 lanes x 32 bytes
 constexpr int WPB = 8;               // warps (chunks) per CTA
 constexpr u32 NOBYTE = 0x100u;
+constexpr int STAGE_BYTES = 1312;   // emission staging per chunk: 1 + 1280 + 1 bytes, padded (+4 for the word reads)
 
 __host__ __device__ __forceinline__ u32 f_of(u32 r) { return r < 4 ? r : 5u; }
 __host__ __device__ __forceinline__ u32 need_of(u32 r) { return r < 3 ? 1u : (r == 3 ? 2u : 0u); }
@@ -280,7 +281,18 @@ __global__ void __launch_bounds__(WPB * 32) rle_emit_kernel(const u8 *__restrict
     u32 k = lo;
     RleBlock bk = blocks[k];
 
-    // pass 2: emit
+    // pass 2: emit.  A chunk that lies inside one block writes one contiguous range of that
+    // block's image (tokens are consecutive; only a count byte at either edge may belong to the
+    // neighbouring chunk), so its bytes are collected in shared memory and stored as aligned words.
+    __shared__ __align__(16) u8 stage_all[WPB][STAGE_BYTES];
+    u8 *stg = stage_all[warp_id()];
+    const bool simple = bk.s <= xc && xc + CH <= bk.c;        // warp-uniform
+    u64 W = 0;                                                // image position of stg[0]
+    if (simple) {
+        const u64 before0 = (xc < bk.e0) ? g_of(xc - bk.s) : bk.u0 + (P[c] - bk.P_e0);
+        W = before0 - 1;                                      // (wraps for the first byte of a block: only differences are used)
+    }
+    u32 wlo = 0xffffffffu, whi = 0;                           // written range, relative to W
     u32 r = r0;
     u64 i = xc + pos0;
 #pragma unroll 4
@@ -306,16 +318,53 @@ __global__ void __launch_bounds__(WPB * 32) rle_emit_kernel(const u8 *__restrict
             before_out = bk.u0 + (Pi - bk.P_e0);
         }
         const bool last_tok = (rb == 254) || (i + 1 == bk.c) || (nb != b);
-        u8 *o = out + bk.rle_off;
-        if (rb < 4) {
-            o[before_out] = (u8)b;
-            if (rb == 3 && last_tok) o[before_out + 1] = 0;
-        } else if (last_tok) {
-            o[before_out - 1] = (u8)(rb - 3);
+        if (simple) {
+            const u32 q = (u32)(before_out - W);
+            if (rb < 4) {
+                stg[q] = (u8)b;
+                wlo = min(wlo, q);
+                whi = max(whi, q + 1);
+                if (rb == 3 && last_tok) {
+                    stg[q + 1] = 0;
+                    whi = max(whi, q + 2);
+                }
+            } else if (last_tok) {
+                stg[q - 1] = (u8)(rb - 3);
+                wlo = min(wlo, q - 1);
+                whi = max(whi, q);
+            }
+        } else {
+            u8 *o = out + bk.rle_off;
+            if (rb < 4) {
+                o[before_out] = (u8)b;
+                if (rb == 3 && last_tok) o[before_out + 1] = 0;
+            } else if (last_tok) {
+                o[before_out - 1] = (u8)(rb - 3);
+            }
         }
         Pi += need_of(r);
         r = (r == 254) ? 0 : r + 1;
     }
+    if (!simple) return;
+    wlo = __reduce_min_sync(0xffffffffu, wlo);
+    whi = __reduce_max_sync(0xffffffffu, whi);
+    if (wlo >= whi) return;                                   // the chunk sits inside one long token
+    __syncwarp();
+    u8 *g = out + bk.rle_off + (W + wlo);                     // first image byte of this chunk
+    const u32 nbytes = whi - wlo;
+    const u32 head = min(nbytes, (u32)((4 - ((uintptr_t)g & 3)) & 3));
+    if (lane < head) g[lane] = stg[wlo + lane];
+    const u32 nwords = (nbytes - head) >> 2;
+    const u32 s0 = wlo + head;                                // stage offset of the first full word
+    const u32 *stg32 = reinterpret_cast<const u32 *>(stg);
+    u32 *g32 = reinterpret_cast<u32 *>(g + head);
+    for (u32 q = lane; q < nwords; q += 32) {
+        const u32 so = s0 + 4 * q;
+        const u32 w0 = stg32[so >> 2], w1 = stg32[(so >> 2) + 1];
+        g32[q] = __funnelshift_r(w0, w1, (so & 3) * 8);
+    }
+    const u32 done = head + 4 * nwords;
+    if (lane < nbytes - done) g[done + lane] = stg[wlo + done + lane];
 }
 
 // ------------------------------------------------------------------ K2: CRC-32/BZIP2
