@@ -79,7 +79,7 @@ struct Device {
     cudaStream_t stream3[3] = {};       // low-priority streams: MTF of finished blocks fills the sort's tail
     // arenas (grown on demand, kept across calls)
     DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, ws_hist, bwt_score, bwt_order;
-    DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, rle_blocks, crc_acc;
+    DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, ch_tiles, rle_blocks, crc_acc;
     DevBuf seg_base, seg_list, seg_cnt, seg_state, num_names, syms, sym_off, sym_len, freqs, mtf_ids, mtf_cseg;
     DevBuf lens, codes, tf, num_tables, num_sel, span_base, hdr, hdr_bits, crc, blk_bits, blk_bitoff,
         total_bits, out;
@@ -211,7 +211,7 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (DevBuf *b : { &d.in, &d.rle, &d.bwt, &d.blk_off, &d.blk_len, &d.ptr, &d.has_byte,
                            &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.ws_hist, &d.bwt_score, &d.bwt_order, &d.ch_lasthead, &d.ch_meta,
-                           &d.ch_restsum, &d.ch_oin, &d.ch_P, &d.rle_blocks, &d.crc_acc, &d.seg_base,
+                           &d.ch_restsum, &d.ch_oin, &d.ch_P, &d.ch_tiles, &d.rle_blocks, &d.crc_acc, &d.seg_base,
                            &d.seg_list, &d.seg_cnt, &d.seg_state, &d.num_names, &d.syms, &d.sym_off,
                            &d.sym_len, &d.freqs, &d.mtf_ids, &d.mtf_cseg, &d.lens, &d.codes, &d.tf, &d.num_tables, &d.num_sel,
                            &d.span_base, &d.hdr, &d.hdr_bits, &d.crc, &d.blk_bits, &d.blk_bitoff,
@@ -560,10 +560,11 @@ static int rle_plan(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const uint8_t 
     CK(ctx, d.ch_restsum.ensure(n_chunks * 4));
     CK(ctx, d.ch_oin.ensure(n_chunks * 8));
     CK(ctx, d.ch_P.ensure((n_chunks + 1) * 8));
+    CK(ctx, d.ch_tiles.ensure(rle_scan_tiles(n_chunks) * 16 + 64));
     CK(ctx, rle_summary_launch(d_in, N, n_chunks, d.ch_lasthead.as<uint64_t>(), d.ch_meta.as<uint32_t>(),
                                d.ch_restsum.as<uint32_t>(), d.ch_oin.as<uint64_t>(), d.ch_P.as<uint64_t>(),
-                               d.stream));
-    d.launches += 2;
+                               d.ch_tiles.as<uint64_t>(), d.stream));
+    d.launches += 4;
     CK(ctx, d.h_P.ensure((n_chunks + 1) * 8));
     CK(ctx, d.h_oin.ensure(n_chunks * 8));
     CK(ctx, cudaMemcpyAsync(d.h_P.p, d.ch_P.p, (n_chunks + 1) * 8, cudaMemcpyDeviceToHost, d.stream));

@@ -138,94 +138,152 @@ __global__ void __launch_bounds__(WPB * 32) rle_summary_kernel(const u8 *__restr
 // start, P[n_chunks] = total.
 constexpr int ST = 1024;
 constexpr int SI = 8;                 // chunks per thread and tile
-__global__ void __launch_bounds__(ST) rle_scan_kernel(const u64 *__restrict__ lasthead, const u32 *__restrict__ meta,
-                                                     const u32 *__restrict__ restsum, u64 n_chunks,
-                                                     u64 *__restrict__ o_in, u64 *__restrict__ P)
+constexpr int STILE = ST * SI;        // chunks per CTA
+
+// block-wide (ST threads) exclusive scans; *total = aggregate of the whole CTA
+__device__ __forceinline__ u64 block_excl_max64(u64 v, u64 *sh, u64 *total)
 {
-    __shared__ u64 sh[40];
-    u64 carry_head = 0, carry_sum = 0;
     const u32 lane = lane_id(), w = warp_id();
-    for (u64 base = 0; base < n_chunks; base += (u64)ST * SI) {
-        const u64 c0 = base + (u64)threadIdx.x * SI;
-        u64 lh[SI];
-        u32 mt[SI], rs[SI];
-        u64 agg = 0;
+    u64 inc = v;
 #pragma unroll
-        for (int k = 0; k < SI; k++) {
-            const bool ok = c0 + k < n_chunks;
-            lh[k] = ok ? lasthead[c0 + k] : 0;
-            mt[k] = ok ? meta[c0 + k] : 0;
-            rs[k] = ok ? restsum[c0 + k] : 0;
-            agg = max(agg, lh[k]);
-        }
-        // block-wide exclusive max scan of the per-thread maxima
-        u64 inc = agg;
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (u32)d) inc = max(inc, t);
+    }
+    u64 ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) ex = 0;
+    if (lane == 31) sh[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        u64 vi = sh[lane];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            u64 t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= (u32)d) inc = max(inc, t);
+            u64 t = __shfl_up_sync(0xffffffffu, vi, d);
+            if (lane >= (u32)d) vi = max(vi, t);
         }
-        u64 ex = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) ex = 0;
-        if (lane == 31) sh[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            u64 vi = sh[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                u64 t = __shfl_up_sync(0xffffffffu, vi, d);
-                if (lane >= (u32)d) vi = max(vi, t);
-            }
-            u64 ve = __shfl_up_sync(0xffffffffu, vi, 1);
-            if (lane == 0) ve = 0;
-            sh[lane] = ve;
-            if (lane == 31) sh[32] = vi;
-        }
-        __syncthreads();
-        u64 hprev = max(max(sh[w], ex), carry_head);
-        const u64 tile_head = sh[32];
-        __syncthreads();
-
-        u64 sv[SI];
-        u64 tsum = 0;
-#pragma unroll
-        for (int k = 0; k < SI; k++) {
-            sv[k] = 0;
-            if (c0 + k < n_chunks) {
-                const u32 lead = mt[k] & 0x7fffffffu;
-                u64 oin = 0;
-                if (mt[k] & 0x80000000u) oin = (c0 + k) * CH - (hprev - 1);
-                const u32 r_in = (u32)(oin % 255u);
-                const u32 t = r_in + lead;
-                sv[k] = 5u * (t / 255u) + f_of(t % 255u) - f_of(r_in) + rs[k];
-                o_in[c0 + k] = oin;
-            }
-            hprev = max(hprev, lh[k]);
-            tsum += sv[k];
-        }
-        // block-wide exclusive sum scan of the per-thread sums
-        const u64 si = warp_incl_sum64(tsum);
-        if (lane == 31) sh[w] = si;
-        __syncthreads();
-        if (w == 0) {
-            u64 v = sh[lane];
-            u64 vi = warp_incl_sum64(v);
-            sh[lane] = vi - v;
-            if (lane == 31) sh[32] = vi;
-        }
-        __syncthreads();
-        u64 pre = carry_sum + sh[w] + si - tsum;
-        const u64 tile_sum = sh[32];
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < SI; k++) {
-            if (c0 + k < n_chunks) P[c0 + k] = pre;
-            pre += sv[k];
-        }
-        carry_sum += tile_sum;
-        carry_head = max(carry_head, tile_head);
+        u64 ve = __shfl_up_sync(0xffffffffu, vi, 1);
+        if (lane == 0) ve = 0;
+        sh[lane] = ve;
+        if (lane == 31) sh[32] = vi;
     }
-    if (threadIdx.x == 0) P[n_chunks] = carry_sum;
+    __syncthreads();
+    const u64 r = max(sh[w], ex);
+    *total = sh[32];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ u64 block_excl_sum64(u64 v, u64 *sh, u64 *total)
+{
+    const u32 lane = lane_id(), w = warp_id();
+    const u64 si = warp_incl_sum64(v);
+    if (lane == 31) sh[w] = si;
+    __syncthreads();
+    if (w == 0) {
+        u64 x = sh[lane];
+        u64 xi = warp_incl_sum64(x);
+        sh[lane] = xi - x;
+        if (lane == 31) sh[32] = xi;
+    }
+    __syncthreads();
+    const u64 r = sh[w] + si - v;
+    *total = sh[32];
+    __syncthreads();
+    return r;
+}
+
+// The chunk tables are two chained scans over the chunks: a running maximum (position of the last
+// run head so far -> run offset o_in at every chunk start), then a running sum of the chunk costs
+// (-> P).  One CTA per tile of STILE chunks, three launches: tile maxima; o_in + tile cost sums
+// (the carry is the maximum over the earlier tiles, at most a few hundred values); P.
+__global__ void __launch_bounds__(ST) rle_scan_heads_kernel(const u64 *__restrict__ lasthead, u64 n_chunks,
+                                                           u64 *__restrict__ tile_head)
+{
+    __shared__ u64 sh[40];
+    const u64 c0 = (u64)blockIdx.x * STILE + (u64)threadIdx.x * SI;
+    u64 agg = 0;
+#pragma unroll
+    for (int k = 0; k < SI; k++)
+        if (c0 + k < n_chunks) agg = max(agg, lasthead[c0 + k]);
+    u64 tot;
+    block_excl_max64(agg, sh, &tot);
+    if (threadIdx.x == 0) tile_head[blockIdx.x] = tot;
+}
+
+// cost of chunk c given the run offset at its start
+__device__ __forceinline__ u64 chunk_cost(u32 mt, u32 rs, u64 oin)
+{
+    const u32 lead = mt & 0x7fffffffu;
+    const u32 r_in = (u32)(oin % 255u);
+    const u32 t = r_in + lead;
+    return 5u * (t / 255u) + f_of(t % 255u) - f_of(r_in) + rs;
+}
+
+__global__ void __launch_bounds__(ST) rle_scan_oin_kernel(const u64 *__restrict__ lasthead, const u32 *__restrict__ meta,
+                                                         const u32 *__restrict__ restsum, u64 n_chunks,
+                                                         const u64 *__restrict__ tile_head, u64 *__restrict__ o_in,
+                                                         u64 *__restrict__ tile_sum)
+{
+    __shared__ u64 sh[40];
+    const u32 t = blockIdx.x;
+    u64 tot;
+    // carry: last run head in the earlier tiles
+    u64 cm = 0;
+    for (u32 q = threadIdx.x; q < t; q += ST) cm = max(cm, tile_head[q]);
+    block_excl_max64(cm, sh, &tot);
+    const u64 carry_head = tot;
+
+    const u64 c0 = (u64)t * STILE + (u64)threadIdx.x * SI;
+    u64 lh[SI];
+    u64 agg = 0;
+#pragma unroll
+    for (int k = 0; k < SI; k++) {
+        lh[k] = (c0 + k < n_chunks) ? lasthead[c0 + k] : 0;
+        agg = max(agg, lh[k]);
+    }
+    u64 hprev = max(block_excl_max64(agg, sh, &tot), carry_head);
+    u64 tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SI; k++) {
+        if (c0 + k < n_chunks) {
+            const u32 mt = meta[c0 + k];
+            u64 oin = 0;
+            if (mt & 0x80000000u) oin = (c0 + k) * CH - (hprev - 1);
+            o_in[c0 + k] = oin;
+            tsum += chunk_cost(mt, restsum[c0 + k], oin);
+        }
+        hprev = max(hprev, lh[k]);
+    }
+    block_excl_sum64(tsum, sh, &tot);
+    if (threadIdx.x == 0) tile_sum[t] = tot;
+}
+
+__global__ void __launch_bounds__(ST) rle_scan_p_kernel(const u32 *__restrict__ meta, const u32 *__restrict__ restsum,
+                                                       const u64 *__restrict__ o_in, u64 n_chunks, u32 n_tiles,
+                                                       const u64 *__restrict__ tile_sum, u64 *__restrict__ P)
+{
+    __shared__ u64 sh[40];
+    const u32 t = blockIdx.x;
+    u64 tot;
+    u64 cs = 0;
+    for (u32 q = threadIdx.x; q < t; q += ST) cs += tile_sum[q];
+    block_excl_sum64(cs, sh, &tot);
+    const u64 carry_sum = tot;
+
+    const u64 c0 = (u64)t * STILE + (u64)threadIdx.x * SI;
+    u64 sv[SI];
+    u64 tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SI; k++) {
+        sv[k] = (c0 + k < n_chunks) ? chunk_cost(meta[c0 + k], restsum[c0 + k], o_in[c0 + k]) : 0;
+        tsum += sv[k];
+    }
+    u64 pre = carry_sum + block_excl_sum64(tsum, sh, &tot);
+#pragma unroll
+    for (int k = 0; k < SI; k++) {
+        if (c0 + k < n_chunks) P[c0 + k] = pre;
+        pre += sv[k];
+    }
+    if (t + 1 == n_tiles && threadIdx.x == 0) P[n_chunks] = carry_sum + tot;
 }
 
 // ------------------------------------------------------------------ kernel 3: emission
@@ -518,13 +576,19 @@ uint32_t crc_finalize(uint32_t acc, uint64_t len)
 
 cudaError_t rle_summary_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks, uint64_t *d_lasthead,
                                uint32_t *d_meta, uint32_t *d_restsum, uint64_t *d_oin, uint64_t *d_P,
-                               cudaStream_t st)
+                               uint64_t *d_tiles, cudaStream_t st)
 {
     unsigned grid = (unsigned)((n_chunks + rle::WPB - 1) / rle::WPB);
     rle::rle_summary_kernel<<<grid, rle::WPB * 32, 0, st>>>(d_in, N, n_chunks, d_lasthead, d_meta, d_restsum);
-    rle::rle_scan_kernel<<<1, rle::ST, 0, st>>>(d_lasthead, d_meta, d_restsum, n_chunks, d_oin, d_P);
+    const unsigned n_tiles = (unsigned)rle_scan_tiles(n_chunks);
+    uint64_t *tile_head = d_tiles, *tile_sum = d_tiles + n_tiles;
+    rle::rle_scan_heads_kernel<<<n_tiles, rle::ST, 0, st>>>(d_lasthead, n_chunks, tile_head);
+    rle::rle_scan_oin_kernel<<<n_tiles, rle::ST, 0, st>>>(d_lasthead, d_meta, d_restsum, n_chunks, tile_head, d_oin, tile_sum);
+    rle::rle_scan_p_kernel<<<n_tiles, rle::ST, 0, st>>>(d_meta, d_restsum, d_oin, n_chunks, n_tiles, tile_sum, d_P);
     return cudaGetLastError();
 }
+
+size_t rle_scan_tiles(uint64_t n_chunks) { return (size_t)((n_chunks + rle::STILE - 1) / rle::STILE); }
 
 cudaError_t rle_emit_launch(const uint8_t *d_in, uint64_t N, uint64_t c_begin, uint64_t c_end,
                             const uint64_t *d_oin, const uint64_t *d_P, const RleBlock *d_blocks,
