@@ -104,7 +104,9 @@ struct bnz_ctx {
     uint8_t *out_cache = nullptr;
     size_t out_cache_cap = 0;
     bool out_cache_lent = false;
-    uint8_t *out_big = nullptr;         // streaming-batch output (ordinary host memory), lent to the caller
+    uint8_t *out_big = nullptr;         // streaming-batch output (ordinary host memory, kept across calls)
+    size_t out_big_cap = 0;
+    bool out_big_lent = false;
     size_t max_batch_bytes = (size_t)3 << 30;   // inputs above this are encoded in streaming batches
     size_t stream_window_bytes = (size_t)512 << 20;   // bnz_stream_*: input bytes per pipeline window
     int open_streams = 0;
@@ -1384,7 +1386,7 @@ extern "C" int bnz_encode(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int le
     if (consumed) *consumed = 0;
     if (level < 1 || level > 9) return fail(ctx, BNZ_EINVAL, "level must be in 1..=9 (lib/lib.rs:89)");
     if (in_len && !in) return BNZ_EINVAL;
-    if (ctx->out_cache_lent || ctx->out_big) return fail(ctx, BNZ_EINVAL, "previous output not released with bnz_free");
+    if (ctx->out_cache_lent || ctx->out_big_lent) return fail(ctx, BNZ_EINVAL, "previous output not released with bnz_free");
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.in_bytes = in_len;
 
@@ -1417,18 +1419,20 @@ extern "C" int bnz_encode(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int le
     } else {
         // ---- streaming batches (inputs larger than one device-resident batch): every batch runs
         // the whole pipeline on the blocks that are complete inside its window; the trailing
-        // partial block is re-read by the next batch.  The stream grows in an ordinary host buffer.
-        size_t cap = 0, pos = 0, win = ctx->max_batch_bytes;
-        auto grow = [&](size_t need) -> bool {
-            if (need <= cap) return true;
-            size_t ncap = std::max(need + need / 4 + 4096, cap * 2);
-            uint8_t *p = static_cast<uint8_t *>(realloc(o, ncap));
-            if (!p) return false;
-            memset(p + cap, 0, ncap - cap);
-            o = p;
-            cap = ncap;
-            return true;
-        };
+        // partial block is re-read by the next batch.  The stream grows in an ordinary host buffer
+        // sized for the worst case up front: untouched pages cost nothing, and nothing is ever
+        // copied or cleared in bulk.
+        size_t pos = 0, win = ctx->max_batch_bytes;
+        const size_t cap = bnz_max_compressed_size(in_len) + 64;
+        if (ctx->out_big_cap < cap) {             // (kept across calls: its pages stay faulted in)
+            free(ctx->out_big);
+            ctx->out_big = static_cast<uint8_t *>(malloc(cap));
+            ctx->out_big_cap = ctx->out_big ? cap : 0;
+        }
+        o = ctx->out_big;
+        if (!o) return fail(ctx, BNZ_ENOMEM, "output buffer");
+        memset(o, 0, 64);
+        auto grow = [&](size_t need) -> bool { return need <= cap; };
         bool first = true;
         while (pos < in_len) {
             const size_t len = std::min(win, in_len - pos);
@@ -1436,35 +1440,25 @@ extern "C" int bnz_encode(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int le
             std::vector<Shard> shards;
             uint64_t used = 0, bits_after = total_bits;
             int rc = encode_all(ctx, in + pos, nullptr, len, level, shards, crcs, &bits_after, final, total_bits, &used);
-            if (rc != BNZ_OK) {
-                free(o);
-                return rc;
-            }
+            if (rc != BNZ_OK) return rc;
             if (shards.empty()) {               // window shorter than one block: widen it
                 if (final) break;
                 win *= 2;
                 continue;
             }
-            if (!grow((size_t)((bits_after + 80 + 7) / 8) + 16)) {
-                free(o);
-                return fail(ctx, BNZ_ENOMEM, "output buffer");
-            }
+            if (!grow((size_t)((bits_after + 80 + 7) / 8) + 16)) return fail(ctx, BNZ_EINTERNAL, "output bound exceeded");
             rc = pack_and_download(ctx, shards, o, first);
-            if (rc != BNZ_OK) {
-                free(o);
-                return rc;
-            }
+            if (rc != BNZ_OK) return rc;
+            // the bytes behind the last (word-rounded) shard must be zero for the next OR-merge / footer
+            memset(o + (size_t)((bits_after + 31) / 32) * 4, 0, 32);
             finish_stats(ctx, shards, true);
             first = false;
             total_bits = bits_after;
             pos += final ? len : (size_t)used;
         }
         nbytes = (size_t)((total_bits + 80 + 7) / 8);
-        if (!grow(nbytes + 16)) {
-            free(o);
-            return fail(ctx, BNZ_ENOMEM, "output buffer");
-        }
-        ctx->out_big = o;
+        if (!grow(nbytes + 16)) return fail(ctx, BNZ_EINTERNAL, "output bound exceeded");
+        ctx->out_big_lent = true;
     }
     // stream header (lib.rs:18-22), footer (lib.rs:66-70), zero padding (out.rs:22-28)
     o[0] = 0x42; o[1] = 0x5A; o[2] = 0x68; o[3] = (uint8_t)('0' + level);
@@ -1481,10 +1475,7 @@ extern "C" void bnz_free(bnz_ctx *ctx, uint8_t *p)
 {
     if (!ctx || !p) return;
     if (p == ctx->out_cache) ctx->out_cache_lent = false;
-    if (p == ctx->out_big) {
-        free(ctx->out_big);
-        ctx->out_big = nullptr;
-    }
+    if (p == ctx->out_big) ctx->out_big_lent = false;
 }
 
 extern "C" int bnz_encode_device(bnz_ctx *ctx, const void *d_in, const uint8_t *h_in, size_t in_len, int level,
