@@ -34,6 +34,24 @@
 namespace bnz {
 namespace bwt {
 
+// Phase timing of the radix pass for tools/bwt_phase_prof.py (`make prof` builds a second library
+// with -DBWT_PHASE_PROF=<thread id>): cycles of thread BWT_PHASE_PROF of every CTA between the
+// marks, summed over the launch.  Compiled out of the product library.
+#ifdef BWT_PHASE_PROF
+__device__ unsigned long long g_prof[8];
+#define PROF_DECL long long prof_t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, prof_prev = clock64(), prof_now
+#define PROF_MARK(i) (prof_now = clock64(), prof_t[i] += prof_now - prof_prev, prof_prev = prof_now)
+#define PROF_FLUSH()                                                                               \
+    do {                                                                                           \
+        if (threadIdx.x == BWT_PHASE_PROF)                                                         \
+            for (int i_ = 0; i_ < 8; i_++) atomicAdd(&g_prof[i_], (unsigned long long)prof_t[i_]); \
+    } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_FLUSH()
+#endif
+
 #ifndef BWT_T
 #define BWT_T 512
 #endif
@@ -321,6 +339,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
     }
     __syncthreads();
 
+    PROF_DECL;
     for (u32 base = 0; base < count; base += TILE) {
         const u32 tile_n = min((u32)TILE, count - base);
         u64 rec[K];
@@ -329,8 +348,10 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             uint4 *row = reinterpret_cast<uint4 *>(sm.whist[w]);
             for (int b = lane; b < WORDS / 4; b += 32) row[b] = make_uint4(0, 0, 0, 0);
         }
+        PROF_MARK(0);                                           // loop overhead + counter zeroing
         mbar_wait(&sm.mbar, phase);
         phase ^= 1u;
+        PROF_MARK(1);                                           // wait for the tile
         const u32 wl = w * (K * 32) + lane;
         if (tile_n == TILE) {
 #pragma unroll
@@ -357,7 +378,9 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             bcount = __shfl_sync(0xffffffffu, bcount, leader);
             rk[k] = ((bcount >> sh) & 0xffffu) + __popc(peers & lanemask_lt());
         }
+        PROF_MARK(2);                                           // ranking
         __syncthreads();                                        // B1: inbuf consumed, whist complete
+        PROF_MARK(3);                                           // wait at B1
 
         if (tid == 0 && base + TILE < count) {                  // prefetch the next tile
             const u32 nb = (min((u32)TILE, count - base - TILE) * 8u + 15u) & ~15u;
@@ -395,6 +418,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             sm.cursor[b0 + 1] = cur1 + hi;
         }
         __syncthreads();                                        // B2
+        PROF_MARK(4);                                           // scan (B1 -> B2)
 
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -403,6 +427,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             sm.stage[pos] = rec[k];
         }
         __syncthreads();                                        // B3
+        PROF_MARK(5);                                           // reorder (B2 -> B3)
 
         if (tile_n == TILE) {
 #pragma unroll
@@ -422,7 +447,9 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             }
         }
         // no barrier here: the next tile's B1 orders these reads before stage/whist are reused
+        PROF_MARK(6);                                           // bucket stores
     }
+    PROF_FLUSH();
     __syncthreads();
 }
 
@@ -772,6 +799,15 @@ __global__ void __launch_bounds__(PT) bwt_predict_kernel(const u8 *__restrict__ 
 }
 
 }  // namespace bwt
+
+#ifdef BWT_PHASE_PROF
+extern "C" __attribute__((visibility("default"))) void bnz_prof_read(unsigned long long *out)
+{
+    unsigned long long z[8] = { 0 };
+    cudaMemcpyFromSymbol(out, bwt::g_prof, sizeof z);
+    cudaMemcpyToSymbol(bwt::g_prof, z, sizeof z);
+}
+#endif
 
 cudaError_t bwt_predict_launch(const uint8_t *d_rle, const uint64_t *d_blk_off, const uint32_t *d_blk_len,
                                uint32_t n_blocks, uint32_t *d_score, cudaStream_t stream)

@@ -49,11 +49,21 @@ BNZ_API const char *bnz_strerror(int code);
 /* human-readable detail of the last failing call on this context ("" if none) */
 BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
 
-/* tunables (call before encoding). keys: "bwt_cluster" (-1 auto | 0 one CTA per block | 2..16 CTAs
- * per block), "bwt_cluster_below" (auto threshold in blocks), "bwt_threads" (512|1024, cluster
- * kernel), "bwt_radix_bits" (8|10, one-CTA kernel), "bwt_ctas_per_sm" (0 = auto),
- * "max_batch_bytes" (inputs above this, default 3 GiB, are encoded in streaming batches so that
- * device memory stays bounded; the stream bytes do not depend on it), "stream_window_bytes" */
+/* tunables (call before encoding). keys:
+ *   "bwt_cluster"        -1 auto | 0 one CTA per block | 2..16 CTAs (one cluster) per block
+ *   "bwt_cluster_below"  auto mode: cluster kernel when a device gets fewer blocks than this (400)
+ *   "bwt_threads"        512 | 1024, cluster kernel
+ *   "bwt_radix_bits"     8 | 10, one-CTA kernel (10 measured slower)
+ *   "bwt_ctas_per_sm"    0 = auto
+ *   "bwt_lpt"            0 index-order work queue | 1 longest-predicted first | 2 light blocks last
+ *   "mtf_overlap"        percent of a device's blocks whose MTF may run beside the sort, in the SM
+ *                        slots its tail leaves empty (70; 0 = strictly after the sort)
+ *   "mtf_groups"         number of block lists the overlapped MTF is issued in (2)
+ *   "crc_low_prio"       1: block CRCs on the low-priority stream (default) | 0: normal side stream
+ *   "max_batch_bytes"    inputs above this (3 GiB) are encoded in batches so that device memory
+ *                        stays bounded
+ *   "stream_window_bytes" bnz_stream_*: input bytes per pinned window (512 MiB)
+ * None of them changes the bytes of the stream. */
 BNZ_API int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value);
 
 /* ---- the hot path --------------------------------------------------------------------

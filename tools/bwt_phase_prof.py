@@ -1,7 +1,7 @@
-"""radix-pass phase times (thread 37 = warp 1 lane 5 of every CTA) from the profiling build
-tools/micro/libbanzai_prof.so: tma wait / rank / B1 wait / scan (B1->B2) / place (B2->B3) / store"""
+"""radix-pass phase times (thread PROF_TID of every CTA, default 37 = warp 1 lane 5) from the profiling
+build tools/micro/libbanzai_prof.so (`make -C banzai_b200/csrc prof [PROF_TID=n]`): tma wait / rank / B1 wait / scan (B1->B2) / place (B2->B3) / store"""
 import sys, os, ctypes as C
-os.environ["BANZAI_B200_LIB"] = os.path.join(os.path.dirname(os.path.abspath(__file__)), "micro", "libbanzai_prof%s.so" % (sys.argv[3] if len(sys.argv) > 3 else "37"))
+os.environ["BANZAI_B200_LIB"] = os.path.join(os.path.dirname(os.path.abspath(__file__)), "micro", "libbanzai_prof.so")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import corpus, banzai_b200
 from banzai_b200 import _ffi
