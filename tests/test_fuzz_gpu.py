@@ -47,3 +47,40 @@ def test_block_boundary_inputs(ctx, seed, tail):
     data = head + tail + bytes([7]) * int(rng.integers(0, 600)) + tail
     got = ctx.encode_bytes(data, 1)
     assert got == O.encode(data, 1)
+
+
+@settings(max_examples=10, deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2 ** 32 - 1), mid=pieces, cuts=st.lists(st.integers(1, 3_000_000), min_size=1, max_size=12))
+def test_streaming_front_end_any_write_sizes(seed, mid, cuts):
+    """bnz_stream_write with fuzzed write sizes over ~3 minimum-size windows at level 1 (the
+    reference's reader-chunk-dependent truncation, SURVEY A-Q4, must not exist here): the stream
+    equals the whole-buffer call, which equals the oracle."""
+    import ctypes as C
+    import banzai_b200
+    from banzai_b200 import _ffi
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(11_000_000, 13_000_000))
+    body = rng.integers(0, 4, n).astype(np.uint8)                     # small alphabet: runs cross windows
+    body[rng.integers(0, n, 2000)] = 200
+    zero_at = int(rng.integers(0, n - 6_000_000))
+    body[zero_at:zero_at + int(rng.integers(0, 6_000_000))] = 0        # a run longer than the headroom of a window
+    data = body.tobytes()[:n // 2] + mid + body.tobytes()[n // 2:]
+    with banzai_b200.Context(n_gpus=1) as c:
+        c.set("stream_window_bytes", 1 << 16)                         # clamped to the minimum (~5.1 MB at level 1)
+        chunks = []
+        cb = _ffi.SINK_FN(lambda u, p, k: chunks.append(bytes((C.c_ubyte * k).from_address(p))) or 0)
+        h = C.c_void_p()
+        assert _ffi.lib.bnz_stream_open(c._h, 1, cb, None, C.byref(h)) == _ffi.OK
+        pos, i = 0, 0
+        while pos < len(data):
+            k = min(cuts[i % len(cuts)], len(data) - pos)
+            assert _ffi.lib.bnz_stream_write(h, data[pos:pos + k], k) == _ffi.OK
+            pos += k
+            i += 1
+        used = C.c_size_t()
+        assert _ffi.lib.bnz_stream_finish(h, C.byref(used)) == _ffi.OK
+        _ffi.lib.bnz_stream_close(h)
+        assert used.value == len(data)
+        got = b"".join(chunks)
+        assert got == c.encode_bytes(data, 1)
+    assert got == O.encode(data, 1)
