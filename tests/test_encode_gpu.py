@@ -161,3 +161,22 @@ def test_streaming_batches_do_not_change_the_stream():
         small = corpus.text(100000)
         assert ctx.encode_bytes(small, 9) == O.encode(small, 9)
         assert ctx.encode_bytes(mixed[:9000000], 3) == O.encode(mixed[:9000000], 3)
+
+
+@pytest.mark.parametrize("sets", [{}, {"mtf_overlap": 95, "mtf_groups": 6}, {"mtf_overlap": 0, "crc_low_prio": 0}],
+                         ids=["default", "many-lists", "serial"])
+def test_overlap_of_sort_tail_with_mtf_and_crc(sets):
+    """more blocks than the one-CTA-per-block sort has CTAs (and than the cluster threshold): the
+    MTF of finished blocks and the block CRCs are queued beside the sort on low-priority streams
+    (DESIGN §5 "Overlap").  Whatever the schedule, the stream is the oracle's."""
+    import banzai_b200
+    data = corpus.mixed(52 * 1000 * 1000)
+    with banzai_b200.Context(n_gpus=1) as c:
+        for k, v in sets.items():
+            c.set(k, v)
+        got = c.encode_bytes(data, 1)
+        assert c.stats()["n_blocks"] > 450
+        again = c.encode_bytes(data, 1)
+    assert got == again
+    assert got == O.encode(data, 1)
+    assert bz2.decompress(got) == data.tobytes()

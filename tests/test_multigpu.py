@@ -42,3 +42,20 @@ def test_all_devices_large_and_tiny():
         # runs crossing shard boundaries
         zeros = bytes(60 << 20) + b"ab" * 3000000 + bytes(30 << 20)
         assert ctx.encode_bytes(zeros, 1) == one.encode_bytes(zeros, 1)
+
+
+@pytest.mark.skipif("_ngpu() < 2")
+def test_streaming_front_end_on_two_devices():
+    """bnz_stream_* windows sharded over two GPUs: same bytes as one bnz_encode on one GPU"""
+    import io
+    import banzai_b200
+    data = corpus.mixed(60 * 1000 * 1000).tobytes()
+    with banzai_b200.Context(n_gpus=1) as one:
+        want = one.encode_bytes(data, 2)
+    with banzai_b200.Context(n_gpus=2) as ctx:
+        ctx.set("stream_window_bytes", 1 << 16)          # minimum-size windows (~10 MB at level 2)
+        sink = io.BytesIO()
+        assert ctx.encode_stream(io.BytesIO(data), sink, 2) == len(data)
+        assert ctx.stats()["n_devices"] == 2
+    assert sink.getvalue() == want
+    assert bz2.decompress(want) == data
