@@ -106,17 +106,29 @@ __global__ void __launch_bounds__(W2 * 32) mtf_compose_kernel(MtfArgs a)
     __syncwarp();
     int cur = 0;
     const u32 nseg = a.seg_base[b + 1] - a.seg_base[b];
+    const u32 seg_first = a.seg_base[b];
+    // the summary of segment s is fetched one step ahead, so that a step costs shared-memory work
+    // only (the dependent global load was most of its latency)
+    u32 cnt_n = 0;
+    uint2 sv_n = make_uint2(0, 0);
+    if (nseg > 1) {
+        cnt_n = a.seg_cnt[seg_first];
+        sv_n = *reinterpret_cast<const uint2 *>(a.seg_list + (size_t)seg_first * 256 + lane * 8);
+    }
     for (u32 s = 0; s < nseg; s++) {
-        const u32 seg = a.seg_base[b] + s;
+        const u32 seg = seg_first + s;
         // the list this segment starts from
         *reinterpret_cast<uint2 *>(a.seg_state + (size_t)seg * 256 + lane * 8) =
             *reinterpret_cast<const uint2 *>(&L[w][cur][lane * 8]);
         if (s + 1 == nseg) break;
-        const u32 cnt = a.seg_cnt[seg];
-        const u8 *sl = a.seg_list + (size_t)seg * 256;
+        const u32 cnt = cnt_n;
+        const uint2 sv = sv_n;
+        if (s + 2 < nseg) {
+            cnt_n = a.seg_cnt[seg + 1];
+            sv_n = *reinterpret_cast<const uint2 *>(a.seg_list + (size_t)(seg + 1) * 256 + lane * 8);
+        }
         if (lane < 8) mask[w][lane] = 0;
         __syncwarp();
-        uint2 sv = *reinterpret_cast<const uint2 *>(sl + lane * 8);
         u32 sw[2] = { sv.x, sv.y };
 #pragma unroll
         for (int k = 0; k < 8; k++) {
