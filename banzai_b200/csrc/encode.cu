@@ -1,0 +1,564 @@
+// encode.cu — bnz_encode / bnz_encode_device: the B200 replacement of the block loop in
+// lib/lib.rs:101-126 (one batch of blocks per call of encode_all, sharded over the devices).
+#include "host.h"
+
+// ---------------------------------------------------------------------------------------
+// bnz_encode: the whole path
+// ---------------------------------------------------------------------------------------
+
+void put_bits_host(uint8_t *buf, uint64_t bitpos, uint64_t value, int nbits)   // MSB first
+{
+    for (int i = nbits - 1; i >= 0; i--, bitpos++)
+        if ((value >> i) & 1) buf[bitpos >> 3] |= (uint8_t)(0x80u >> (bitpos & 7));
+}
+
+// One device's share of a bnz_encode call: a contiguous range of blocks.
+// in_base/oin_base/P_base: see rle_emit_shard.
+static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t N, const uint64_t *oin_base,
+                       const uint64_t *P_base, int level)
+{
+    Device &d = *sh.d;
+    uint64_t rle_total = 0;
+    int rc = rle_emit_shard(ctx, d, in_base, N, oin_base, P_base, sh.blocks, nullptr, &rle_total);
+    if (rc != BNZ_OK) return rc;
+    CK(ctx, cudaEventRecord(d.ev[2], d.stream));
+    const uint32_t nb = (uint32_t)sh.blocks.size();
+    Batch &bt = sh.bt;
+    bt.blk_off.resize(nb);
+    bt.blk_len.resize(nb);
+    for (uint32_t b = 0; b < nb; b++) {
+        bt.blk_off[b] = sh.blocks[b].rle_off;
+        bt.blk_len[b] = sh.blocks[b].n;
+    }
+    bt.bytes_total = rle_total;
+    bt.build();
+    rc = upload_batch(ctx, d, bt);
+    if (rc != BNZ_OK) return rc;
+
+    // K3/K4
+    CK(ctx, d.bwt.ensure(rle_total));
+    CK(ctx, d.ptr.ensure((size_t)nb * 4));
+    CK(ctx, d.has_byte.ensure((size_t)nb * 256));
+    CK(ctx, d.bwt_stats.ensure((size_t)nb * sizeof(BwtStats)));
+    if (sh.bwt_after) {
+        while (sh.bwt_after->bwt_recorded.load(std::memory_order_acquire) == 0) std::this_thread::yield();
+        if (sh.bwt_after->bwt_recorded.load() > 0) CK(ctx, cudaStreamWaitEvent(d.stream, sh.bwt_after->d->ev[3], 0));
+        CK(ctx, cudaEventRecord(d.ev[2], d.stream));       // RLE stage ends where the sort may start
+    }
+    // MTF arenas and the completion flags are set up before the sort is launched (allocation
+    // would synchronise with it)
+    rc = mtf_ensure(ctx, d, bt);
+    if (rc != BNZ_OK) return rc;
+    CK(ctx, d.h_done.ensure((size_t)nb * 4));
+    volatile uint32_t *h_done = d.h_done.as<uint32_t>();
+    memset(d.h_done.p, 0, (size_t)nb * 4);
+    uint32_t *d_done = nullptr;
+    CK(ctx, cudaHostGetDevicePointer((void **)&d_done, d.h_done.p, 0));
+    CK(ctx, cudaEventRecord(d.ev[12], d.stream));
+    bool armed = false;
+    rc = run_bwt_device(ctx, d, d.rle.as<uint8_t>(), d.bwt.as<uint8_t>(), d.blk_off.as<uint64_t>(),
+                        d.blk_len.as<uint32_t>(), nb, bt.max_len, d.ptr.as<uint32_t>(), d.has_byte.as<uint8_t>(),
+                        d.bwt_stats.as<BwtStats>(), ctx->mtf_overlap > 0 ? d_done : nullptr, &armed);
+    if (rc != BNZ_OK) {
+        sh.bwt_recorded.store(-1, std::memory_order_release);
+        return rc;
+    }
+    CK(ctx, cudaEventRecord(d.ev[3], d.stream));
+    sh.bwt_recorded.store(1, std::memory_order_release);
+
+    // K5 (the RLE1 images are dead once their block is sorted: their buffer holds the MTF index
+    // bytes).  The one-CTA-per-block sort ends in a long tail (blocks differ 5x in cost and only
+    // ~4 fit per CTA), so the MTF of the blocks that finish first runs beside it: the sort raises a
+    // host-visible flag per finished block, and as soon as a leading group of blocks is complete
+    // this thread queues its MTF on a low-priority stream, whose CTAs get the SM slots the sort
+    // leaves empty.
+    std::vector<uint32_t> list;
+    std::vector<uint8_t> taken(nb, 0);
+    uint32_t ids_used = 0, lists_used = 0;
+    if (armed) {
+        for (cudaStream_t st : d.stream3) CK(ctx, cudaStreamWaitEvent(st, d.ev[12], 0));
+        const uint32_t budget = (uint32_t)((uint64_t)nb * (uint32_t)ctx->mtf_overlap / 100);   // blocks that may go beside the sort
+        const uint32_t step = std::max<uint32_t>(32, budget / (uint32_t)ctx->mtf_groups);
+        uint32_t n_over = 0;
+        int g = 0;
+        list.reserve(nb);
+        while (n_over < budget) {
+            for (uint32_t b = 0; b < nb && list.size() < step; b++)
+                if (!taken[b] && h_done[b]) {
+                    taken[b] = 1;
+                    list.push_back(b);
+                }
+            if (list.size() >= step) {
+                std::atomic_thread_fence(std::memory_order_acquire);
+                rc = run_mtf_list(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>(), list.data(),
+                                  (uint32_t)list.size(), ids_used, lists_used, d.stream3[g++ % 3]);
+                if (rc != BNZ_OK) return rc;
+                n_over += (uint32_t)list.size();
+                list.clear();
+                continue;
+            }
+            if (cudaEventQuery(d.ev[3]) != cudaErrorNotReady) break;       // the sort ended (or failed)
+            std::this_thread::yield();
+        }
+        for (int k = 0; k < 3; k++) CK(ctx, cudaEventRecord(d.ev[13 + k], d.stream3[k]));
+    }
+    // everything not queued beside the sort follows it on the main stream
+    for (uint32_t b = 0; b < nb; b++)
+        if (!taken[b]) list.push_back(b);      // (a partly gathered list is already in `list`)
+    rc = run_mtf_list(ctx, d, bt, d.bwt.as<uint8_t>(), d.rle.as<uint8_t>(), d.has_byte.as<uint8_t>(), list.data(),
+                      (uint32_t)list.size(), ids_used, lists_used, d.stream);
+    if (rc != BNZ_OK) return rc;
+    if (armed)
+        for (int k = 0; k < 3; k++) CK(ctx, cudaStreamWaitEvent(d.stream, d.ev[13 + k], 0));
+    CK(ctx, cudaEventRecord(d.ev[4], d.stream));
+
+    // K6/K7 + headers + block bit lengths (the headers need the block CRCs from the side stream)
+    CK(ctx, cudaStreamWaitEvent(d.stream, d.ev[10], 0));
+    rc = run_huff_model_device(ctx, d, bt, level, 1, 0, 0, sh.ha);
+    if (rc != BNZ_OK) return rc;
+    sh.bst.resize(nb);
+    sh.crcs.resize(nb);
+    CK(ctx, cudaMemcpyAsync(sh.crcs.data(), d.crc.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaMemcpyAsync(&sh.block_bits, d.total_bits.p, 8, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaMemcpyAsync(sh.bst.data(), d.bwt_stats.p, (size_t)nb * sizeof(BwtStats), cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaEventRecord(d.ev[5], d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    return BNZ_OK;
+}
+
+// K8 for one shard once its global bit offset is known.  The shard's bits land in d.out such
+// that d.out word 0 is global word (bit_base / 32).
+static int shard_pack(bnz_ctx *ctx, Shard &sh, size_t *out_bytes)
+{
+    Device &d = *sh.d;
+    const uint64_t local_base = sh.bit_base & 31;
+    const size_t bytes = (size_t)((local_base + sh.block_bits + 31) / 32) * 4;
+    *out_bytes = bytes;
+    CK(ctx, d.out.ensure(bytes + 256));
+    CK(ctx, cudaMemsetAsync(d.out.p, 0, ((bytes + 127) & ~(size_t)63), d.stream));
+    sh.ha.out_words = d.out.as<uint32_t>();
+    sh.ha.bit_base = local_base;
+    CK(ctx, huff_rescan_launch(sh.ha, d.stream, &d.launches));
+    CK(ctx, huff_pack_launch(sh.ha, d.stream, &d.launches));
+    CK(ctx, cudaEventRecord(d.ev[6], d.stream));
+    return BNZ_OK;
+}
+
+static void add_stats(bnz_stats &st, const Shard &sh)
+{
+    st.n_blocks += (uint32_t)sh.blocks.size();
+    for (const BwtStats &b : sh.bst) {
+        st.bwt_n += b.n;
+        st.bwt_sum_active += b.sum_active;
+        st.bwt_sum_active_passes += b.sum_active_passes;
+        st.bwt_rounds_total += b.rounds;
+        st.bwt_max_rounds = std::max(st.bwt_max_rounds, b.rounds);
+        st.bwt_tied_blocks += b.tied;
+        st.bwt_cyc_build += b.cyc_build;
+        st.bwt_cyc_radix += b.cyc_radix;
+        st.bwt_cyc_rerank += b.cyc_rerank;
+    }
+    st.bwt_algorithmic_bytes = 9 * st.bwt_n + 16 * st.bwt_sum_active_passes + 36 * st.bwt_sum_active;
+    st.kernel_launches += sh.d->launches;
+}
+
+void finish_stats(bnz_ctx *ctx, std::vector<Shard> &shards, bool have_d2h)
+{
+    // per batch: max over the shards (they run concurrently); batches add up
+    bnz_stats &st = ctx->stats;
+    float h2d = 0, rle = 0, bwt = 0, mtf = 0, huff = 0, pack = 0, d2h = 0, total = 0;
+    for (Shard &sh : shards) {
+        if (sh.blocks.empty()) continue;
+        Device &d = *sh.d;
+        cudaSetDevice(d.id);
+        auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, d.ev[a], d.ev[b]); return ms; };
+        h2d = std::max(h2d, el(0, 1));
+        rle = std::max(rle, el(1, 2));
+        bwt = std::max(bwt, el(2, 3));
+        mtf = std::max(mtf, el(3, 4));
+        huff = std::max(huff, el(4, 5));
+        pack = std::max(pack, el(5, 6));
+        if (have_d2h) d2h = std::max(d2h, el(6, 7));
+        total = std::max(total, el(0, have_d2h ? 7 : 6));
+    }
+    st.h2d_ms += h2d;
+    st.rle_ms += rle;
+    st.bwt_ms += bwt;
+    st.mtf_ms += mtf;
+    st.huff_ms += huff;
+    st.pack_ms += pack;
+    st.d2h_ms += d2h;
+    st.total_ms += total;
+    st.n_devices = std::max<uint32_t>(st.n_devices, (uint32_t)shards.size());
+    st.bwt_radix_bits = (uint32_t)ctx->radix_bits;
+}
+
+uint32_t fold_stream_crc(const std::vector<uint32_t> &crcs)       // lib.rs:108
+{
+    uint32_t s = 0;
+    for (uint32_t c : crcs) s = c ^ ((s << 1) | (s >> 31));
+    return s;
+}
+
+static int ensure_out_cache(bnz_ctx *ctx, size_t nbytes)
+{
+    if (ctx->out_cache_cap < nbytes + 16) {
+        if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
+        ctx->out_cache = nullptr;
+        ctx->out_cache_cap = 0;
+        size_t want = nbytes + nbytes / 4 + 4096;
+        CK(ctx, cudaHostAlloc((void **)&ctx->out_cache, want, cudaHostAllocPortable));
+        ctx->out_cache_cap = want;
+    }
+    return BNZ_OK;
+}
+
+// contiguous block ranges with ~equal RLE1 bytes per device
+static std::vector<uint32_t> split_blocks(const std::vector<RleBlock> &blocks, size_t n_dev)
+{
+    std::vector<uint32_t> cut(n_dev + 1, 0);
+    uint64_t total = 0;
+    for (const RleBlock &b : blocks) total += b.n;
+    uint64_t acc = 0;
+    size_t g = 1;
+    for (uint32_t i = 0; i < blocks.size() && g < n_dev; i++) {
+        acc += blocks[i].n;
+        while (g < n_dev && acc * n_dev >= total * g) cut[g++] = i + 1;
+    }
+    for (; g <= n_dev; g++) cut[g] = (uint32_t)blocks.size();
+    return cut;
+}
+
+// One batch of the path: the blocks that can be cut from h_in[0, N).  d_in0: optional device copy
+// already resident on device 0.  `final`: no input follows (otherwise the trailing incomplete
+// block is left for the next batch; *consumed tells where it starts).  `bit_base`: bit offset of
+// the batch's first block in the stream.  Leaves every shard's bits in its device's d.out and
+// returns the layout; the callers move the bytes.
+int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, size_t N, int level,
+               std::vector<Shard> &shards, std::vector<uint32_t> &crcs, uint64_t *total_bits, bool final,
+               uint64_t bit_base, uint64_t *consumed)
+{
+    Device &d0 = ctx->devs[0];
+    bnz_stats &st = ctx->stats;
+    for (Device &d : ctx->devs) d.launches = 0;
+    CK(ctx, cudaSetDevice(d0.id));
+    CK(ctx, cudaEventRecord(d0.ev[0], d0.stream));
+    const uint8_t *d_in = d_in0;
+    if (!d_in) {
+        CK(ctx, d0.in.ensure(N + 64));
+        CK(ctx, cudaMemcpyAsync(d0.in.p, h_in, N, cudaMemcpyHostToDevice, d0.stream));
+        d_in = d0.in.as<uint8_t>();
+        st.h2d_bytes += N;
+    }
+    CK(ctx, cudaEventRecord(d0.ev[1], d0.stream));
+
+    std::vector<RleBlock> blocks;
+    int rc = rle_plan(ctx, d0, d_in, h_in, N, level, blocks, final, consumed);
+    if (rc != BNZ_OK) return rc;
+    if (blocks.empty()) {               // (non-final batch shorter than one block)
+        shards.clear();
+        *total_bits = bit_base;
+        return BNZ_OK;
+    }
+
+    CK(ctx, cudaEventRecord(d0.ev[8], d0.stream));       // input + chunk tables resident on device 0
+    const size_t n_dev = std::min(ctx->devs.size(), std::max<size_t>(1, blocks.size()));
+    std::vector<uint32_t> cut = split_blocks(blocks, n_dev);
+    shards = std::vector<Shard>(n_dev);
+    for (size_t g = 0; g < n_dev; g++) {
+        Shard &sh = shards[g];
+        sh.d = &ctx->devs[g];
+        if (g > 0 && ctx->devs[g].id == ctx->devs[g - 1].id) sh.bwt_after = &shards[g - 1];
+        sh.blocks.assign(blocks.begin() + cut[g], blocks.begin() + cut[g + 1]);
+        const uint64_t off0 = sh.blocks.empty() ? 0 : sh.blocks.front().rle_off;
+        for (RleBlock &b : sh.blocks) b.rle_off -= off0;
+    }
+
+    const uint64_t *h_P = d0.h_P.as<uint64_t>(), *h_oin = d0.h_oin.as<uint64_t>();
+    auto work = [&](size_t g) -> int {
+        Shard &sh = shards[g];
+        Device &d = *sh.d;
+        if (sh.blocks.empty()) {
+            sh.bwt_recorded.store(-1, std::memory_order_release);
+            return BNZ_OK;
+        }
+        CK(ctx, cudaSetDevice(d.id));
+        if (d.id == d0.id) {
+            // same physical GPU (lane 0, or an extra lane that overlaps its stages with the other
+            // lanes' kernels): the input and the chunk tables are already resident
+            if (g != 0) {
+                CK(ctx, cudaStreamWaitEvent(d.stream, d0.ev[8], 0));
+                CK(ctx, cudaEventRecord(d.ev[0], d.stream));
+                CK(ctx, cudaEventRecord(d.ev[1], d.stream));
+            }
+            return shard_model(ctx, sh, d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
+        }
+        // other devices: make their input range and chunk tables resident
+        CK(ctx, cudaEventRecord(d.ev[0], d.stream));
+        const uint64_t c0 = sh.blocks.front().s / RLE_CHUNK;
+        const uint64_t c1 = (sh.blocks.back().c + RLE_CHUNK - 1) / RLE_CHUNK;
+        const uint64_t a = c0 ? c0 * RLE_CHUNK - 16 : 0;
+        const uint64_t b = std::min<uint64_t>(N, c1 * RLE_CHUNK + 16);
+        CK(ctx, d.in.ensure(b - a + 64));
+        CK(ctx, cudaMemcpyAsync(d.in.p, h_in + a, b - a, cudaMemcpyHostToDevice, d.stream));
+        CK(ctx, d.ch_oin.ensure((c1 - c0 + 1) * 8));
+        CK(ctx, d.ch_P.ensure((c1 - c0 + 2) * 8));
+        CK(ctx, cudaMemcpyAsync(d.ch_oin.p, h_oin + c0, (c1 - c0) * 8, cudaMemcpyHostToDevice, d.stream));
+        CK(ctx, cudaMemcpyAsync(d.ch_P.p, h_P + c0, (c1 - c0 + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+        CK(ctx, cudaEventRecord(d.ev[1], d.stream));
+        return shard_model(ctx, sh, d.in.as<uint8_t>() - a, N, d.ch_oin.as<uint64_t>() - c0, d.ch_P.as<uint64_t>() - c0, level);
+    };
+
+    if (n_dev == 1) {
+        rc = work(0);
+        if (rc != BNZ_OK) return rc;
+    } else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < n_dev; g++)
+            th.emplace_back([&, g]() {
+                t_err_sink = &shards[g].err;
+                shards[g].rc = work(g);
+                if (shards[g].bwt_recorded.load() == 0) shards[g].bwt_recorded.store(-1, std::memory_order_release);
+                t_err_sink = nullptr;
+            });
+        for (std::thread &t : th) t.join();
+        for (Shard &sh : shards)
+            if (sh.rc != BNZ_OK) {
+                ctx->err = sh.err;
+                return sh.rc;
+            }
+    }
+
+    // bit offsets of the shards (blocks are concatenated at bit granularity, lib.rs:101-126 + out.rs)
+    uint64_t bits = bit_base;
+    for (Shard &sh : shards) {
+        sh.bit_base = bits;
+        bits += sh.block_bits;
+        crcs.insert(crcs.end(), sh.crcs.begin(), sh.crcs.end());
+    }
+    *total_bits = bits;
+    for (Shard &sh : shards) add_stats(st, sh);
+    return BNZ_OK;
+}
+
+// pack every shard of a batch at its bit phase and copy it to host memory `o` (the stream buffer,
+// byte 0 = stream byte 0).  `stream_start`: the batch begins right after the 32-bit stream header,
+// so its first word is not shared with earlier data.  (The streaming front end passes a buffer
+// that starts at stream byte `o_first_byte`, a multiple of 4.)
+int pack_and_download(bnz_ctx *ctx, std::vector<Shard> &shards, uint8_t *o, bool stream_start,
+                      size_t o_first_byte)
+{
+    std::vector<uint32_t> first_word(shards.size(), 0);
+    for (size_t g = 0; g < shards.size(); g++) {
+        Shard &sh = shards[g];
+        if (sh.blocks.empty()) continue;
+        Device &d = *sh.d;
+        CK(ctx, cudaSetDevice(d.id));
+        size_t bytes = 0;
+        int rc = shard_pack(ctx, sh, &bytes);
+        if (rc != BNZ_OK) return rc;
+        const size_t w0 = (size_t)(sh.bit_base >> 5) * 4 - o_first_byte;
+        if (g == 0 && stream_start) {
+            CK(ctx, cudaMemcpyAsync(o + w0, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
+        } else {
+            CK(ctx, cudaMemcpyAsync(&first_word[g], d.out.p, 4, cudaMemcpyDeviceToHost, d.stream));
+            if (bytes > 4)
+                CK(ctx, cudaMemcpyAsync(o + w0 + 4, d.out.as<uint8_t>() + 4, bytes - 4, cudaMemcpyDeviceToHost, d.stream));
+        }
+        CK(ctx, cudaEventRecord(d.ev[7], d.stream));
+        ctx->stats.d2h_bytes += bytes;
+    }
+    for (Shard &sh : shards) {
+        if (sh.blocks.empty()) continue;
+        CK(ctx, cudaSetDevice(sh.d->id));
+        CK(ctx, cudaStreamSynchronize(sh.d->stream));
+    }
+    // merge the words shared with the previous shard / batch
+    for (size_t g = 0; g < shards.size(); g++) {
+        if (shards[g].blocks.empty() || (g == 0 && stream_start)) continue;
+        uint8_t *w = o + ((size_t)(shards[g].bit_base >> 5) * 4 - o_first_byte);
+        const uint8_t *f = reinterpret_cast<const uint8_t *>(&first_word[g]);
+        if ((shards[g].bit_base & 31) == 0) memcpy(w, f, 4);
+        else for (int k = 0; k < 4; k++) w[k] |= f[k];
+    }
+    return BNZ_OK;
+}
+
+extern "C" int bnz_encode(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int level, uint8_t **out,
+                          size_t *out_len, size_t *consumed)
+{
+    if (!ctx || !out || !out_len) return BNZ_EINVAL;
+    *out = nullptr;
+    *out_len = 0;
+    if (consumed) *consumed = 0;
+    if (level < 1 || level > 9) return fail(ctx, BNZ_EINVAL, "level must be in 1..=9 (lib/lib.rs:89)");
+    if (in_len && !in) return BNZ_EINVAL;
+    if (ctx->out_cache_lent || ctx->out_big_lent) return fail(ctx, BNZ_EINVAL, "previous output not released with bnz_free");
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->stats.in_bytes = in_len;
+
+    uint64_t total_bits = 32;
+    std::vector<uint32_t> crcs;
+    uint8_t *o = nullptr;
+    size_t nbytes = 0;
+
+    if (in_len <= ctx->max_batch_bytes) {
+        // ---- one batch: the stream is assembled in the context's pinned buffer
+        std::vector<Shard> shards;
+        if (in_len > 0) {
+            int rc = encode_all(ctx, in, nullptr, in_len, level, shards, crcs, &total_bits);
+            if (rc != BNZ_OK) return rc;
+        }
+        nbytes = (size_t)((total_bits + 80 + 7) / 8);
+        int rc = ensure_out_cache(ctx, nbytes + 8);
+        if (rc != BNZ_OK) return rc;
+        o = ctx->out_cache;
+        if (in_len > 0) {
+            rc = pack_and_download(ctx, shards, o, true);
+            if (rc != BNZ_OK) return rc;
+            const size_t written = (size_t)((total_bits + 31) / 32) * 4;
+            if (written < nbytes + 8) memset(o + written, 0, nbytes + 8 - written);
+            finish_stats(ctx, shards, true);
+        } else {
+            memset(o, 0, nbytes + 8);
+        }
+        ctx->out_cache_lent = true;
+    } else {
+        // ---- streaming batches (inputs larger than one device-resident batch): every batch runs
+        // the whole pipeline on the blocks that are complete inside its window; the trailing
+        // partial block is re-read by the next batch.  The stream grows in an ordinary host buffer
+        // sized for the worst case up front: untouched pages cost nothing, and nothing is ever
+        // copied or cleared in bulk.
+        size_t pos = 0, win = ctx->max_batch_bytes;
+        const size_t cap = bnz_max_compressed_size(in_len) + 64;
+        if (ctx->out_big_cap < cap) {             // (kept across calls: its pages stay faulted in)
+            free(ctx->out_big);
+            ctx->out_big = static_cast<uint8_t *>(malloc(cap));
+            ctx->out_big_cap = ctx->out_big ? cap : 0;
+        }
+        o = ctx->out_big;
+        if (!o) return fail(ctx, BNZ_ENOMEM, "output buffer");
+        memset(o, 0, 64);
+        auto grow = [&](size_t need) -> bool { return need <= cap; };
+        bool first = true;
+        while (pos < in_len) {
+            const size_t len = std::min(win, in_len - pos);
+            const bool final = pos + len == in_len;
+            std::vector<Shard> shards;
+            uint64_t used = 0, bits_after = total_bits;
+            int rc = encode_all(ctx, in + pos, nullptr, len, level, shards, crcs, &bits_after, final, total_bits, &used);
+            if (rc != BNZ_OK) return rc;
+            if (shards.empty()) {               // window shorter than one block: widen it
+                if (final) break;
+                win *= 2;
+                continue;
+            }
+            if (!grow((size_t)((bits_after + 80 + 7) / 8) + 16)) return fail(ctx, BNZ_EINTERNAL, "output bound exceeded");
+            rc = pack_and_download(ctx, shards, o, first);
+            if (rc != BNZ_OK) return rc;
+            // the bytes behind the last (word-rounded) shard must be zero for the next OR-merge / footer
+            memset(o + (size_t)((bits_after + 31) / 32) * 4, 0, 32);
+            finish_stats(ctx, shards, true);
+            first = false;
+            total_bits = bits_after;
+            pos += final ? len : (size_t)used;
+        }
+        nbytes = (size_t)((total_bits + 80 + 7) / 8);
+        if (!grow(nbytes + 16)) return fail(ctx, BNZ_EINTERNAL, "output bound exceeded");
+        ctx->out_big_lent = true;
+    }
+    // stream header (lib.rs:18-22), footer (lib.rs:66-70), zero padding (out.rs:22-28)
+    o[0] = 0x42; o[1] = 0x5A; o[2] = 0x68; o[3] = (uint8_t)('0' + level);
+    put_bits_host(o, total_bits, 0x177245385090ull, 48);
+    put_bits_host(o, total_bits + 48, fold_stream_crc(crcs), 32);
+    ctx->stats.out_bytes = nbytes;
+    *out = o;
+    *out_len = nbytes;
+    if (consumed) *consumed = in_len;
+    return BNZ_OK;
+}
+
+extern "C" void bnz_free(bnz_ctx *ctx, uint8_t *p)
+{
+    if (!ctx || !p) return;
+    if (p == ctx->out_cache) ctx->out_cache_lent = false;
+    if (p == ctx->out_big) ctx->out_big_lent = false;
+}
+
+extern "C" int bnz_encode_device(bnz_ctx *ctx, const void *d_in, const uint8_t *h_in, size_t in_len, int level,
+                                 void *d_out, size_t d_out_cap, size_t *out_len)
+{
+    if (!ctx || !out_len || !d_out) return BNZ_EINVAL;
+    *out_len = 0;
+    if (level < 1 || level > 9) return fail(ctx, BNZ_EINVAL, "level must be in 1..=9 (lib/lib.rs:89)");
+    if (in_len == 0 || !d_in || !h_in) return BNZ_EINVAL;
+    for (Device &dv : ctx->devs)
+        if (dv.id != ctx->devs[0].id) return fail(ctx, BNZ_EINVAL, "bnz_encode_device needs a single-GPU context");
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->stats.in_bytes = in_len;
+    Device &d = ctx->devs[0];
+    uint64_t total_bits = 32;
+    std::vector<uint32_t> crcs;
+    std::vector<Shard> shards;
+    int rc = encode_all(ctx, h_in, (const uint8_t *)d_in, in_len, level, shards, crcs, &total_bits);
+    if (rc != BNZ_OK) return rc;
+    const size_t nbytes = (size_t)((total_bits + 80 + 7) / 8);
+    if (nbytes + 8 > d_out_cap) return fail(ctx, BNZ_EINVAL, "d_out_cap too small");
+    uint8_t *dst = static_cast<uint8_t *>(d_out);
+
+    // every lane packs at its bit phase and copies device-to-device; a word shared by two lanes
+    // is merged through the host (4 bytes)
+    std::vector<uint32_t> first_word(shards.size(), 0);
+    for (size_t g = 0; g < shards.size(); g++) {
+        Shard &sh = shards[g];
+        if (sh.blocks.empty()) continue;
+        Device &dl = *sh.d;
+        size_t bytes = 0;
+        rc = shard_pack(ctx, sh, &bytes);
+        if (rc != BNZ_OK) return rc;
+        const size_t w0 = (size_t)(sh.bit_base >> 5) * 4;
+        if (g == 0) {
+            CK(ctx, cudaMemcpyAsync(dst + w0, dl.out.p, bytes, cudaMemcpyDeviceToDevice, dl.stream));
+        } else {
+            CK(ctx, cudaMemcpyAsync(&first_word[g], dl.out.p, 4, cudaMemcpyDeviceToHost, dl.stream));
+            if (bytes > 4)
+                CK(ctx, cudaMemcpyAsync(dst + w0 + 4, dl.out.as<uint8_t>() + 4, bytes - 4, cudaMemcpyDeviceToDevice, dl.stream));
+        }
+    }
+    for (Shard &sh : shards)
+        if (!sh.blocks.empty()) CK(ctx, cudaStreamSynchronize(sh.d->stream));
+    for (size_t g = 1; g < shards.size(); g++) {
+        if (shards[g].blocks.empty()) continue;
+        uint8_t *w = dst + (size_t)(shards[g].bit_base >> 5) * 4;
+        uint32_t cur = 0;
+        if (shards[g].bit_base & 31) {
+            CK(ctx, cudaMemcpyAsync(&cur, w, 4, cudaMemcpyDeviceToHost, d.stream));
+            CK(ctx, cudaStreamSynchronize(d.stream));
+        }
+        cur |= first_word[g];
+        CK(ctx, cudaMemcpyAsync(w, &cur, 4, cudaMemcpyHostToDevice, d.stream));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+    }
+    // header, and the footer patched over the last partial byte
+    uint8_t tail[16] = { 0 };
+    const uint64_t tb = total_bits & 7;
+    const size_t last = (size_t)(total_bits >> 3);
+    uint8_t lastbyte = 0;
+    if (tb) {
+        CK(ctx, cudaMemcpyAsync(&lastbyte, dst + last, 1, cudaMemcpyDeviceToHost, d.stream));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+    }
+    tail[0] = lastbyte;
+    put_bits_host(tail, tb, 0x177245385090ull, 48);
+    put_bits_host(tail, tb + 48, fold_stream_crc(crcs), 32);
+    const uint8_t head[4] = { 0x42, 0x5A, 0x68, (uint8_t)('0' + level) };
+    CK(ctx, cudaMemcpyAsync(dst, head, 4, cudaMemcpyHostToDevice, d.stream));
+    CK(ctx, cudaMemcpyAsync(dst + last, tail, nbytes - last, cudaMemcpyHostToDevice, d.stream));
+    for (Shard &sh : shards)
+        if (!sh.blocks.empty()) CK(ctx, cudaEventRecord(sh.d->ev[7], sh.d->stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    finish_stats(ctx, shards, false);
+    ctx->stats.out_bytes = nbytes;
+    *out_len = nbytes;
+    return BNZ_OK;
+}

@@ -1,4 +1,4 @@
-// kernels.h — internal interface between the host pipeline (pipeline.cu) and the kernel
+// kernels.h — internal interface between the host pipeline (context.cu, stages.cu, encode.cu, stream.cu; shared declarations in host.h) and the kernel
 // translation units.  Nothing here is part of the public C ABI (include/banzai_b200.h).
 #pragma once
 #include <cuda_runtime.h>
