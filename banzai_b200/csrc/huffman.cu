@@ -178,10 +178,15 @@ __device__ __forceinline__ void heap_extract(HeapMem &h, u32 &len, u16 &id_out, 
     h.id[idx - 1] = lid;
 }
 
-constexpr int BW = 4;            // warps per CTA
+// The reference retries the whole build with the weights halved until no code is longer than 17
+// bits (huffman.rs:271-298); large blocks need several tries.  The tries are independent, so
+// NTRY lanes replay the heap for scaling 1, 2, 4, ... at the same time (each in its own heap) and
+// the lowest scaling that fits wins — the same table the sequential retry loop ends with.
+constexpr int BW = 1;            // warps (jobs) per CTA
+constexpr int NTRY = 8;          // scalings tried at once
 __global__ void __launch_bounds__(BW * 32) huff_build_kernel(HuffArgs a)
 {
-    __shared__ HeapMem mem[BW];
+    __shared__ HeapMem mem[BW][NTRY];
     __shared__ u32 fr[BW][MAXS];
     const u32 w = warp_id(), lane = lane_id();
     const u32 job = blockIdx.x * BW + w;
@@ -201,13 +206,16 @@ __global__ void __launch_bounds__(BW * 32) huff_build_kernel(HuffArgs a)
     __syncwarp();
     u8 *lens = a.lens + ((size_t)b * MAXT + t) * MAXS;
     u32 *codes = a.codes + ((size_t)b * MAXT + t) * MAXS;
-    if (lane == 0) {
-        HeapMem &h = mem[w];
-        u32 scaling = 1;
-        for (;;) {                                       // huffman.rs:271-298
+
+    u32 winner = 0;
+    for (u32 round = 0;; round++) {
+        bool fits = false;
+        if (lane < NTRY) {
+            HeapMem &h = mem[w][lane];
+            const u32 shift = round * NTRY + lane;           // scaling = 2^shift
             u32 len = 0;
             for (u32 s = 0; s < num_syms; s++)
-                heap_insert(h, len, (u16)(s + 1), ((u64)(fr[w][s] / scaling + 1)) << 8);
+                heap_insert(h, len, (u16)(s + 1), ((u64)((shift < 32 ? fr[w][s] >> shift : 0u) + 1)) << 8);
             u32 nodes = num_syms + 1;                    // root (0) + leaves (1..n)
             for (;;) {
                 u16 i1, i2;
@@ -232,25 +240,38 @@ __global__ void __launch_bounds__(BW * 32) huff_build_kernel(HuffArgs a)
                 h.depth[idn] = (u8)d;
                 if (idn <= num_syms && d > maxd) maxd = d;
             }
-            if (maxd <= MAXLEN) break;
-            scaling <<= 1;
+            fits = maxd <= MAXLEN;
         }
+        const u32 ok = __ballot_sync(0xffffffffu, fits);
+        if (ok) {
+            winner = __ffs(ok) - 1;                          // the smallest scaling that fits
+            break;
+        }
+    }
+    __syncwarp();
+    const HeapMem &h = mem[w][winner];
+    for (u32 s = lane; s < MAXS; s += 32) lens[s] = (s < num_syms) ? h.depth[s + 1] : (u8)0;
+    if (lane == 0) {
+        // canonical codes (huffman.rs:550-561): per length, symbols in ascending order get consecutive
+        // words; the word doubles from one length to the next
+        u32 cnt[MAXLEN + 2], first[MAXLEN + 2];
+        for (u32 l = 0; l <= MAXLEN + 1; l++) cnt[l] = 0;
         u32 minl = 255, maxl = 0;
-        for (u32 s = 0; s < MAXS; s++) {
-            u32 l = (s < num_syms) ? h.depth[s + 1] : 0;
-            lens[s] = (u8)l;
-            if (s < num_syms) { minl = min(minl, l); maxl = max(maxl, l); }
+        for (u32 s = 0; s < num_syms; s++) {
+            const u32 l = h.depth[s + 1];
+            cnt[l]++;
+            minl = min(minl, l);
+            maxl = max(maxl, l);
         }
-        // canonical codes, huffman.rs:550-561
         u32 word = 0;
         for (u32 l = minl; l <= maxl; l++) {
-            for (u32 s = 0; s < num_syms; s++) {
-                if (h.depth[s + 1] == l) {
-                    codes[s] = (l << 24) | word;
-                    word++;
-                }
-            }
-            word <<= 1;
+            first[l] = word;
+            word = (word + cnt[l]) << 1;
+            cnt[l] = 0;
+        }
+        for (u32 s = 0; s < num_syms; s++) {
+            const u32 l = h.depth[s + 1];
+            codes[s] = (l << 24) | (first[l] + cnt[l]++);
         }
     }
 }
