@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(WPB * 32) rle_emit_kernel(const u8 *__restrict
 
     // pass 1: this lane's cost, then the warp prefix -> P at the lane start
     u32 cost = 0;
+    bool long_run = false;              // some byte of this lane is the 4th or a later byte of its run
     {
         u32 r = r0;
 #pragma unroll
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(WPB * 32) rle_emit_kernel(const u8 *__restrict
             if ((u32)j < lb.valid) {
                 if (hm & (1u << j)) r = 0;
                 cost += need_of(r);
+                long_run |= r >= 3;
                 r = (r == 254) ? 0 : r + 1;
             }
         }
@@ -351,10 +353,21 @@ __global__ void __launch_bounds__(WPB * 32) rle_emit_kernel(const u8 *__restrict
         W = before0 - 1;                                      // (wraps for the first byte of a block: only differences are used)
     }
     u32 wlo = 0xffffffffu, whi = 0;                           // written range, relative to W
+    // no run reaches four bytes anywhere in the chunk (and the chunk lies behind the block's first
+    // run): every byte is a literal, the image is the input shifted — copy the words
+    const bool literal = simple && xc >= bk.e0 && !__any_sync(0xffffffffu, long_run);
+    if (literal) {
+        W += 1;                                               // stg[0] is the chunk's first byte
+        u32 *stg32w = reinterpret_cast<u32 *>(stg);
+#pragma unroll
+        for (int k = 0; k < 8; k++) stg32w[lane * 8 + k] = lb.w[k];
+        wlo = 0;
+        whi = CH;
+    }
     u32 r = r0;
     u64 i = xc + pos0;
 #pragma unroll 4
-    for (int j = 0; j < 32; j++, i++) {
+    for (int j = 0; j < 32 && !literal; j++, i++) {
         if ((u32)j >= lb.valid) break;
         if (hm & (1u << j)) r = 0;
         while (i >= bk.c && k + 1 < n_blocks) { k++; bk = blocks[k]; }
