@@ -84,6 +84,7 @@ lib.bnz_memcpy_h2d.argtypes = [_vp, _vp, _vp, _sz]
 lib.bnz_memcpy_d2h.argtypes = [_vp, _vp, _vp, _sz]
 lib.bnz_get_stats.argtypes = [_vp, C.POINTER(Stats)]
 lib.bnz_stage_rle1.argtypes = [_vp, _vp, _sz, C.c_int, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _szp]
+lib.bnz_host_cut_chain.argtypes = [_vp, _sz, C.c_int, _vp, _vp, _sz, C.c_int, _vp, _vp, _vp, _sz, _szp, _szp]
 lib.bnz_stage_bwt.argtypes = [_vp, _vp, _vp, _vp, _sz, C.c_int, _vp, _vp, _vp, _vp]
 lib.bnz_stage_mtf.argtypes = [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]
 lib.bnz_stage_huffman.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp]
@@ -94,5 +95,5 @@ EXPORTS = [
     "bnz_encode_file", "bnz_host_alloc", "bnz_host_free", "bnz_device_alloc", "bnz_device_free",
     "bnz_memcpy_h2d", "bnz_memcpy_d2h", "bnz_get_stats", "bnz_stage_rle1", "bnz_stage_bwt",
     "bnz_stage_mtf", "bnz_stage_huffman", "bnz_stream_open", "bnz_stream_reserve", "bnz_stream_commit",
-    "bnz_stream_write", "bnz_stream_finish", "bnz_stream_close",
+    "bnz_stream_write", "bnz_stream_finish", "bnz_stream_close", "bnz_host_cut_chain",
 ]

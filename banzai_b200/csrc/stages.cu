@@ -280,6 +280,32 @@ static int run_rle_device(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const ui
     return rle_emit_shard(ctx, d, d_in, N, d.ch_oin.as<uint64_t>(), d.ch_P.as<uint64_t>(), blocks, &crcs, rle_total);
 }
 
+// The host part of K1 on its own (no device needed): the sequential cut chain over chunk tables
+// the caller supplies.  Lets the cut rule (lib/rle.rs:121-240, SURVEY A-Q1) be checked on a CPU.
+extern "C" int bnz_host_cut_chain(const uint8_t *in, size_t in_len, int level, const uint64_t *P,
+                                  const uint64_t *o_in, size_t n_chunks, int final, uint64_t *blk_in_off,
+                                  uint64_t *blk_in_len, uint32_t *blk_rle_len, size_t max_blocks, size_t *n_blocks,
+                                  size_t *consumed)
+{
+    if (!n_blocks || level < 1 || level > 9 || (in_len && (!in || !P || !o_in))) return BNZ_EINVAL;
+    *n_blocks = 0;
+    if (consumed) *consumed = 0;
+    if (in_len == 0) return BNZ_OK;
+    if (n_chunks != (in_len + RLE_CHUNK - 1) / RLE_CHUNK) return BNZ_EINVAL;
+    std::vector<RleBlock> blocks;
+    uint64_t used = 0;
+    if (rle_walk_cuts(in, in_len, level, P, o_in, n_chunks, blocks, final != 0, &used) != 0) return BNZ_EINTERNAL;
+    if (blocks.size() > max_blocks) return BNZ_EINVAL;
+    for (size_t b = 0; b < blocks.size(); b++) {
+        if (blk_in_off) blk_in_off[b] = blocks[b].s;
+        if (blk_in_len) blk_in_len[b] = blocks[b].c - blocks[b].s;
+        if (blk_rle_len) blk_rle_len[b] = blocks[b].n;
+    }
+    *n_blocks = blocks.size();
+    if (consumed) *consumed = (size_t)used;
+    return BNZ_OK;
+}
+
 extern "C" int bnz_stage_rle1(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int level, uint64_t *blk_in_off,
                               uint64_t *blk_in_len, uint64_t *blk_rle_off, uint32_t *blk_rle_len,
                               uint32_t *blk_crc, size_t max_blocks, uint8_t *rle_out, size_t rle_cap,

@@ -170,6 +170,18 @@ BNZ_API int bnz_stage_rle1(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int l
                            uint32_t *blk_rle_len, uint32_t *blk_crc, size_t max_blocks,
                            uint8_t *rle_out, size_t rle_cap, size_t *n_blocks);
 
+/* The host half of that stage alone, no device involved: the sequential cut chain
+ * (`encode` calling `rle_one` block after block, lib/lib.rs:101-126 with the capacity rule of
+ * lib/rle.rs:121-240) over chunk tables supplied by the caller.  For every 1 KiB chunk c of the
+ * input: o_in[c] = run offset of its first byte (number of equal bytes directly before it),
+ * P[c] = RLE1 bytes emitted for in[0 .. 1024 c) when no block is ever cut (P has n_chunks + 1
+ * entries).  final == 0: more input follows, a block that only ends with the data is not
+ * reported.  *consumed = input bytes covered by the reported blocks. */
+BNZ_API int bnz_host_cut_chain(const uint8_t *in, size_t in_len, int level, const uint64_t *P,
+                               const uint64_t *o_in, size_t n_chunks, int final,
+                               uint64_t *blk_in_off, uint64_t *blk_in_len, uint32_t *blk_rle_len,
+                               size_t max_blocks, size_t *n_blocks, size_t *consumed);
+
 /* `bwt::bwt` (lib/bwt.rs:526) on n_blocks independent blocks stored back to back:
  * block b = blocks[blk_off[b] .. blk_off[b] + blk_len[b]).  Outputs use the same layout.
  * has_byte is [n_blocks][256]. max block length = 100000*level. */
