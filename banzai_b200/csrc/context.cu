@@ -30,6 +30,52 @@ extern "C" const char *bnz_strerror(int code)
 
 extern "C" const char *bnz_last_error(const bnz_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
 
+// streams, events of one lane on device `id` (arenas grow on demand)
+bool device_init(Device &d, int id)
+{
+    d.id = id;
+    cudaDeviceProp prop;
+    int prio_lo = 0, prio_hi = 0;
+    bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaGetDeviceProperties(&prop, d.id) == cudaSuccess &&
+              prop.major >= 10 &&        // kernels are built for sm_100a only; fail loudly
+              cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess &&
+              // the sort's persistent CTAs must win every SM slot over the work that fills its tail
+              cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&d.stream2, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&d.stream3[0], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&d.stream3[1], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&d.stream3[2], cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+    for (cudaEvent_t &e : d.ev)
+        if (ok && cudaEventCreate(&e) != cudaSuccess) ok = false;
+    if (ok) d.sm_count = prop.multiProcessorCount;
+    return ok;
+}
+
+void device_release(Device &d)
+{
+    cudaSetDevice(d.id);
+    if (d.stream) cudaStreamSynchronize(d.stream);
+    for (DevBuf *b : { &d.in, &d.rle, &d.bwt, &d.blk_off, &d.blk_len, &d.ptr, &d.has_byte,
+                       &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.ws_hist, &d.bwt_score, &d.bwt_order, &d.ch_lasthead, &d.ch_meta,
+                       &d.ch_restsum, &d.ch_oin, &d.ch_P, &d.ch_tiles, &d.rle_blocks, &d.crc_acc, &d.seg_base,
+                       &d.seg_list, &d.seg_cnt, &d.seg_state, &d.num_names, &d.syms, &d.sym_off,
+                       &d.sym_len, &d.freqs, &d.mtf_ids, &d.mtf_cseg, &d.lens, &d.codes, &d.tf, &d.num_tables, &d.num_sel,
+                       &d.span_base, &d.hdr, &d.hdr_bits, &d.crc, &d.blk_bits, &d.blk_bitoff,
+                       &d.total_bits, &d.out })
+        b->release();
+    for (cudaEvent_t e : d.ev)
+        if (e) cudaEventDestroy(e);
+    d.h_P.release();
+    d.h_oin.release();
+    d.h_acc.release();
+    d.h_done.release();
+    d.h_mtf.release();
+    if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.stream2) cudaStreamDestroy(d.stream2);
+    for (cudaStream_t st : d.stream3)
+        if (st) cudaStreamDestroy(st);
+}
+
 extern "C" void bnz_ctx_destroy(bnz_ctx *ctx);
 
 extern "C" int bnz_ctx_create_on(bnz_ctx **out, const int *device_ids, int n_devices)
@@ -46,26 +92,10 @@ extern "C" int bnz_ctx_create_on(bnz_ctx **out, const int *device_ids, int n_dev
     for (int i = 0; i < n_devices; i++) {
         // a device id may repeat: every entry is an independent lane (own streams and arenas)
         ctx->devs.emplace_back();
-        Device &d = ctx->devs.back();
-        d.id = device_ids[i];
-        cudaDeviceProp prop;
-        int prio_lo = 0, prio_hi = 0;
-        bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaGetDeviceProperties(&prop, d.id) == cudaSuccess &&
-                  prop.major >= 10 &&        // kernels are built for sm_100a only; fail loudly
-                  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess &&
-                  // the sort's persistent CTAs must win every SM slot over the work that fills its tail
-                  cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
-                  cudaStreamCreateWithPriority(&d.stream2, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
-                  cudaStreamCreateWithPriority(&d.stream3[0], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
-                  cudaStreamCreateWithPriority(&d.stream3[1], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
-                  cudaStreamCreateWithPriority(&d.stream3[2], cudaStreamNonBlocking, prio_lo) == cudaSuccess;
-        for (cudaEvent_t &e : d.ev)
-            if (ok && cudaEventCreate(&e) != cudaSuccess) ok = false;
-        if (!ok) {
+        if (!device_init(ctx->devs.back(), device_ids[i])) {
             bnz_ctx_destroy(ctx);
             return BNZ_ECUDA;
         }
-        d.sm_count = prop.multiProcessorCount;
     }
     *out = ctx;
     return BNZ_OK;
@@ -85,28 +115,10 @@ extern "C" int bnz_ctx_create(bnz_ctx **out, int n_gpus)
 extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
 {
     if (!ctx) return;
-    for (Device &d : ctx->devs) {
-        cudaSetDevice(d.id);
-        if (d.stream) cudaStreamSynchronize(d.stream);
-        for (DevBuf *b : { &d.in, &d.rle, &d.bwt, &d.blk_off, &d.blk_len, &d.ptr, &d.has_byte,
-                           &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.ws_hist, &d.bwt_score, &d.bwt_order, &d.ch_lasthead, &d.ch_meta,
-                           &d.ch_restsum, &d.ch_oin, &d.ch_P, &d.ch_tiles, &d.rle_blocks, &d.crc_acc, &d.seg_base,
-                           &d.seg_list, &d.seg_cnt, &d.seg_state, &d.num_names, &d.syms, &d.sym_off,
-                           &d.sym_len, &d.freqs, &d.mtf_ids, &d.mtf_cseg, &d.lens, &d.codes, &d.tf, &d.num_tables, &d.num_sel,
-                           &d.span_base, &d.hdr, &d.hdr_bits, &d.crc, &d.blk_bits, &d.blk_bitoff,
-                           &d.total_bits, &d.out })
-            b->release();
-        for (cudaEvent_t e : d.ev)
-            if (e) cudaEventDestroy(e);
-        d.h_P.release();
-        d.h_oin.release();
-        d.h_acc.release();
-        d.h_done.release();
-        d.h_mtf.release();
-        if (d.stream) cudaStreamDestroy(d.stream);
-        if (d.stream2) cudaStreamDestroy(d.stream2);
-        for (cudaStream_t st : d.stream3)
-            if (st) cudaStreamDestroy(st);
+    for (Device &d : ctx->devs) device_release(d);
+    if (ctx->aux) {
+        device_release(*ctx->aux);
+        delete ctx->aux;
     }
     if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
     free(ctx->out_big);
@@ -133,6 +145,16 @@ extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
     }
     if (!strcmp(key, "crc_low_prio")) {
         ctx->crc_low_prio = value != 0;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "piece_blocks_per_sm_x16")) {
+        if (value < 1 || value > 64) return BNZ_EINVAL;
+        ctx->piece_blocks_per_sm_x16 = (int)value;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "h2d_overlap")) {
+        if (value < 0 || value > 2) return BNZ_EINVAL;
+        ctx->h2d_overlap = (int)value;      // 0 off | 1 auto | 2 forced even for small inputs (tests)
         return BNZ_OK;
     }
     if (!strcmp(key, "mtf_groups")) {

@@ -229,6 +229,135 @@ static std::vector<uint32_t> split_blocks(const std::vector<RleBlock> &blocks, s
     return cut;
 }
 
+// One GPU, host input, many blocks: the input is uploaded and cut in two pieces.  The first piece
+// holds a little more than one block per CTA of the sort; its blocks are sorted (lane 0) while the
+// rest is still on the PCIe bus.  The chunk tables of the second piece continue the first's (the
+// scan carries are kept per tile), the host walk is simply repeated over the whole input (1 us per
+// block) and must reproduce the first piece's blocks; the remaining blocks run on a second lane of
+// the same device, whose sort CTAs take the SM slots the first launch frees.  *handled = false:
+// the input is too small for this, nothing was done.
+static int encode_pieces(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level, std::vector<Shard> &shards,
+                         std::vector<uint32_t> &crcs, uint64_t *total_bits, uint64_t bit_base, bool *handled)
+{
+    *handled = false;
+    Device &d0 = ctx->devs[0];
+    const uint64_t n_chunks = (N + RLE_CHUNK - 1) / RLE_CHUNK;
+    const uint64_t tile = rle_scan_tile_chunks();
+    const uint64_t blk = (uint64_t)100000 * level;
+    // piece A: about one block per SM (rounded up to whole scan tiles).  Its sort CTAs then leave
+    // half of every SM free, so the RLE kernels of the second piece can run as soon as its bytes
+    // have arrived (behind a launch with two CTAs on every SM they waited ~25 ms for the first
+    // blocks to finish), and one CTA per SM already sorts at 87 % of the rate of two.
+    const uint64_t slots = (uint64_t)d0.sm_count * (uint64_t)ctx->piece_blocks_per_sm_x16 / 16;
+    uint64_t cA = ((slots * blk / RLE_CHUNK + tile - 1) / tile) * tile;
+    if (ctx->h2d_overlap == 2) {                              // forced (tests): one scan tile, whatever the size
+        cA = tile;
+        if (cA * RLE_CHUNK * 2 > N) return BNZ_OK;
+    } else if (cA * RLE_CHUNK * 4 > N || N < ((size_t)256 << 20)) {
+        return BNZ_OK;                                        // too little to hide: the copy is short, two lanes cost latency
+    }
+    const uint64_t bytesA = std::min<uint64_t>(N, cA * RLE_CHUNK + 4096);
+    if (!ctx->aux) {
+        ctx->aux = new Device();
+        if (!device_init(*ctx->aux, d0.id)) {
+            device_release(*ctx->aux);
+            delete ctx->aux;
+            ctx->aux = nullptr;
+            return fail(ctx, BNZ_ECUDA, "second lane");
+        }
+    }
+    Device &d1 = *ctx->aux;
+    *handled = true;
+    bnz_stats &st = ctx->stats;
+    d0.launches = d1.launches = 0;
+    CK(ctx, cudaSetDevice(d0.id));
+    CK(ctx, d0.in.ensure(N + 64));
+    CK(ctx, d0.ch_lasthead.ensure(n_chunks * 8));
+    CK(ctx, d0.ch_meta.ensure(n_chunks * 4));
+    CK(ctx, d0.ch_restsum.ensure(n_chunks * 4));
+    CK(ctx, d0.ch_oin.ensure(n_chunks * 8));
+    CK(ctx, d0.ch_P.ensure((n_chunks + 1) * 8));
+    CK(ctx, d0.ch_tiles.ensure(rle_scan_tiles(n_chunks) * 16 + 64));
+    CK(ctx, d0.h_P.ensure((n_chunks + 1) * 8));
+    CK(ctx, d0.h_oin.ensure(n_chunks * 8));
+    uint8_t *d_in = d0.in.as<uint8_t>();
+    uint64_t *h_P = d0.h_P.as<uint64_t>(), *h_oin = d0.h_oin.as<uint64_t>();
+
+    // ---- piece A on lane 0; the copy of piece B is queued right behind it on lane 1's stream
+    CK(ctx, cudaEventRecord(d0.ev[0], d0.stream));
+    CK(ctx, cudaMemcpyAsync(d_in, h_in, bytesA, cudaMemcpyHostToDevice, d0.stream));
+    CK(ctx, cudaEventRecord(d0.ev[1], d0.stream));
+    CK(ctx, cudaEventRecord(d1.ev[0], d1.stream));
+    CK(ctx, cudaMemcpyAsync(d_in + bytesA, h_in + bytesA, N - bytesA, cudaMemcpyHostToDevice, d1.stream));
+    CK(ctx, cudaEventRecord(d1.ev[1], d1.stream));
+    st.h2d_bytes += N;
+    CK(ctx, rle_summary_range_launch(d_in, N, n_chunks, 0, cA, d0.ch_lasthead.as<uint64_t>(), d0.ch_meta.as<uint32_t>(),
+                                     d0.ch_restsum.as<uint32_t>(), d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(),
+                                     d0.ch_tiles.as<uint64_t>(), d0.stream));
+    d0.launches += 4;
+    CK(ctx, cudaMemcpyAsync(h_P, d0.ch_P.p, (cA + 1) * 8, cudaMemcpyDeviceToHost, d0.stream));
+    CK(ctx, cudaMemcpyAsync(h_oin, d0.ch_oin.p, cA * 8, cudaMemcpyDeviceToHost, d0.stream));
+    CK(ctx, cudaStreamSynchronize(d0.stream));
+    std::vector<RleBlock> blocksA;
+    uint64_t usedA = 0;
+    if (rle_walk_cuts(h_in, cA * RLE_CHUNK, level, h_P, h_oin, cA, blocksA, false, &usedA) != 0)
+        return fail(ctx, BNZ_EINTERNAL, "RLE1 cut walk failed");
+    CK(ctx, cudaEventRecord(d0.ev[8], d0.stream));
+
+    shards = std::vector<Shard>(2);
+    shards[0].d = &d0;
+    shards[1].d = &d1;
+    shards[0].blocks = blocksA;
+    std::thread tA([&]() {
+        t_err_sink = &shards[0].err;
+        shards[0].rc = blocksA.empty() ? BNZ_OK
+                                       : shard_model(ctx, shards[0], d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
+        t_err_sink = nullptr;
+    });
+
+    // ---- piece B: tables of the remaining chunks (lane 1's stream, behind its copy), whole walk
+    int rc = BNZ_OK;
+    auto pieceB = [&]() -> int {
+        CK(ctx, cudaSetDevice(d0.id));
+        CK(ctx, rle_summary_range_launch(d_in, N, n_chunks, cA, n_chunks, d0.ch_lasthead.as<uint64_t>(),
+                                         d0.ch_meta.as<uint32_t>(), d0.ch_restsum.as<uint32_t>(), d0.ch_oin.as<uint64_t>(),
+                                         d0.ch_P.as<uint64_t>(), d0.ch_tiles.as<uint64_t>(), d1.stream));
+        d1.launches += 4;
+        CK(ctx, cudaMemcpyAsync(h_P + cA, d0.ch_P.as<uint64_t>() + cA, (n_chunks + 1 - cA) * 8, cudaMemcpyDeviceToHost, d1.stream));
+        CK(ctx, cudaMemcpyAsync(h_oin + cA, d0.ch_oin.as<uint64_t>() + cA, (n_chunks - cA) * 8, cudaMemcpyDeviceToHost, d1.stream));
+        CK(ctx, cudaStreamSynchronize(d1.stream));
+        std::vector<RleBlock> all;
+        uint64_t used = 0;
+        if (rle_walk_cuts(h_in, N, level, h_P, h_oin, n_chunks, all, true, &used) != 0 || all.size() < blocksA.size())
+            return fail(ctx, BNZ_EINTERNAL, "RLE1 cut walk failed");
+        for (size_t b = 0; b < blocksA.size(); b++)
+            if (all[b].s != blocksA[b].s || all[b].c != blocksA[b].c || all[b].n != blocksA[b].n || all[b].rle_off != blocksA[b].rle_off)
+                return fail(ctx, BNZ_EINTERNAL, "cut chain of the first piece is not a prefix of the whole");
+        shards[1].blocks.assign(all.begin() + blocksA.size(), all.end());
+        if (shards[1].blocks.empty()) return BNZ_OK;
+        const uint64_t off0 = shards[1].blocks.front().rle_off;
+        for (RleBlock &b : shards[1].blocks) b.rle_off -= off0;
+        return shard_model(ctx, shards[1], d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
+    };
+    rc = pieceB();
+    tA.join();
+    if (shards[0].rc != BNZ_OK) {
+        ctx->err = shards[0].err;
+        return shards[0].rc;
+    }
+    if (rc != BNZ_OK) return rc;
+
+    uint64_t bits = bit_base;
+    for (Shard &sh : shards) {
+        sh.bit_base = bits;
+        bits += sh.block_bits;
+        crcs.insert(crcs.end(), sh.crcs.begin(), sh.crcs.end());
+    }
+    *total_bits = bits;
+    for (Shard &sh : shards) add_stats(st, sh);
+    return BNZ_OK;
+}
+
 // One batch of the path: the blocks that can be cut from h_in[0, N).  d_in0: optional device copy
 // already resident on device 0.  `final`: no input follows (otherwise the trailing incomplete
 // block is left for the next batch; *consumed tells where it starts).  `bit_base`: bit offset of
@@ -240,6 +369,14 @@ int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, size_t N
 {
     Device &d0 = ctx->devs[0];
     bnz_stats &st = ctx->stats;
+    if (ctx->h2d_overlap && ctx->devs.size() == 1 && !d_in0 && final && N >= ((size_t)16 << 20)) {
+        bool handled = false;
+        int rc = encode_pieces(ctx, h_in, N, level, shards, crcs, total_bits, bit_base, &handled);
+        if (rc != BNZ_OK || handled) {
+            if (handled && consumed) *consumed = N;
+            return rc;
+        }
+    }
     for (Device &d : ctx->devs) d.launches = 0;
     CK(ctx, cudaSetDevice(d0.id));
     CK(ctx, cudaEventRecord(d0.ev[0], d0.stream));

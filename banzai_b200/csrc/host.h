@@ -111,6 +111,9 @@ struct bnz_ctx {
     size_t max_batch_bytes = (size_t)3 << 30;   // inputs above this are encoded in streaming batches
     size_t stream_window_bytes = (size_t)512 << 20;   // bnz_stream_*: input bytes per pipeline window
     int open_streams = 0;
+    Device *aux = nullptr;             // second lane on the first device (created on demand): the blocks of a late-arriving input piece
+    int piece_blocks_per_sm_x16 = 17;  // size of the first piece in blocks per SM (x 1/16)
+    int h2d_overlap = 1;               // one device, host input: upload in two pieces, sort the first while the second arrives
     int crc_low_prio = 1;              // block CRCs on the low-priority stream (they would delay the start of the sort)
     int mtf_groups = 2;
     int mtf_overlap = 70;              // percent of a device's blocks whose MTF may run beside the sort (0: off)
@@ -119,6 +122,8 @@ struct bnz_ctx {
 
 // worker threads of a multi-device encode record their error text in their own string
 extern thread_local std::string *t_err_sink;
+bool device_init(Device &d, int id);
+void device_release(Device &d);
 void set_err(bnz_ctx *ctx, const std::string &msg);
 int fail(bnz_ctx *ctx, int code, const std::string &msg);
 

@@ -31,6 +31,10 @@ struct RleBlock {                 // one bzip2 block as cut by the host walk
 cudaError_t crc_upload_tables();
 uint32_t crc_finalize(uint32_t acc, uint64_t len);
 size_t rle_scan_tiles(uint64_t n_chunks);
+uint64_t rle_scan_tile_chunks();
+cudaError_t rle_summary_range_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks_total, uint64_t c_first,
+                                     uint64_t c_last, uint64_t *d_lasthead, uint32_t *d_meta, uint32_t *d_restsum,
+                                     uint64_t *d_oin, uint64_t *d_P, uint64_t *d_tiles, cudaStream_t st);
 cudaError_t rle_summary_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks, uint64_t *d_lasthead,
                                uint32_t *d_meta, uint32_t *d_restsum, uint64_t *d_oin, uint64_t *d_P,
                                uint64_t *d_tiles /* 2 * rle_scan_tiles(n_chunks) words of scratch */,

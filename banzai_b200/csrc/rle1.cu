@@ -79,11 +79,12 @@ __device__ __forceinline__ u32 head_mask(const LaneBytes &lb)
 }
 
 // ------------------------------------------------------------------ kernel 1: chunk summaries
-__global__ void __launch_bounds__(WPB * 32) rle_summary_kernel(const u8 *__restrict__ in, u64 N, u64 n_chunks,
-                                                              u64 *__restrict__ lasthead,
+__global__ void __launch_bounds__(WPB * 32) rle_summary_kernel(const u8 *__restrict__ in, u64 N, u64 c_first,
+                                                              u64 n_chunks, u64 *__restrict__ lasthead,
                                                               u32 *__restrict__ meta, u32 *__restrict__ restsum)
 {
-    const u64 c = (u64)blockIdx.x * WPB + warp_id();
+    // chunks [c_first, n_chunks)
+    const u64 c = c_first + (u64)blockIdx.x * WPB + warp_id();
     if (c >= n_chunks) return;
     const u32 lane = lane_id();
     const u64 xc = c * CH;
@@ -195,18 +196,19 @@ __device__ __forceinline__ u64 block_excl_sum64(u64 v, u64 *sh, u64 *total)
 // run head so far -> run offset o_in at every chunk start), then a running sum of the chunk costs
 // (-> P).  One CTA per tile of STILE chunks, three launches: tile maxima; o_in + tile cost sums
 // (the carry is the maximum over the earlier tiles, at most a few hundred values); P.
-__global__ void __launch_bounds__(ST) rle_scan_heads_kernel(const u64 *__restrict__ lasthead, u64 n_chunks,
+__global__ void __launch_bounds__(ST) rle_scan_heads_kernel(const u64 *__restrict__ lasthead, u64 n_chunks, u32 tile0,
                                                            u64 *__restrict__ tile_head)
 {
     __shared__ u64 sh[40];
-    const u64 c0 = (u64)blockIdx.x * STILE + (u64)threadIdx.x * SI;
+    const u32 tile = tile0 + blockIdx.x;
+    const u64 c0 = (u64)tile * STILE + (u64)threadIdx.x * SI;
     u64 agg = 0;
 #pragma unroll
     for (int k = 0; k < SI; k++)
         if (c0 + k < n_chunks) agg = max(agg, lasthead[c0 + k]);
     u64 tot;
     block_excl_max64(agg, sh, &tot);
-    if (threadIdx.x == 0) tile_head[blockIdx.x] = tot;
+    if (threadIdx.x == 0) tile_head[tile] = tot;
 }
 
 // cost of chunk c given the run offset at its start
@@ -219,12 +221,12 @@ __device__ __forceinline__ u64 chunk_cost(u32 mt, u32 rs, u64 oin)
 }
 
 __global__ void __launch_bounds__(ST) rle_scan_oin_kernel(const u64 *__restrict__ lasthead, const u32 *__restrict__ meta,
-                                                         const u32 *__restrict__ restsum, u64 n_chunks,
+                                                         const u32 *__restrict__ restsum, u64 n_chunks, u32 tile0,
                                                          const u64 *__restrict__ tile_head, u64 *__restrict__ o_in,
                                                          u64 *__restrict__ tile_sum)
 {
     __shared__ u64 sh[40];
-    const u32 t = blockIdx.x;
+    const u32 t = tile0 + blockIdx.x;
     u64 tot;
     // carry: last run head in the earlier tiles
     u64 cm = 0;
@@ -258,11 +260,12 @@ __global__ void __launch_bounds__(ST) rle_scan_oin_kernel(const u64 *__restrict_
 }
 
 __global__ void __launch_bounds__(ST) rle_scan_p_kernel(const u32 *__restrict__ meta, const u32 *__restrict__ restsum,
-                                                       const u64 *__restrict__ o_in, u64 n_chunks, u32 n_tiles,
-                                                       const u64 *__restrict__ tile_sum, u64 *__restrict__ P)
+                                                       const u64 *__restrict__ o_in, u64 n_chunks, u32 tile0,
+                                                       u32 n_tiles, const u64 *__restrict__ tile_sum,
+                                                       u64 *__restrict__ P)
 {
     __shared__ u64 sh[40];
-    const u32 t = blockIdx.x;
+    const u32 t = tile0 + blockIdx.x;
     u64 tot;
     u64 cs = 0;
     for (u32 q = threadIdx.x; q < t; q += ST) cs += tile_sum[q];
@@ -587,19 +590,35 @@ uint32_t crc_finalize(uint32_t acc, uint64_t len)
     return acc ^ rle::gf_mul(0xFFFFFFFFu, p) ^ 0xFFFFFFFFu;
 }
 
+// chunk tables for chunks [c_first, c_last) of an input of n_chunks_total chunks; c_first must be
+// a multiple of the scan tile (rle_scan_tile_chunks()).  The tables of the chunks before c_first
+// (and their tile aggregates in d_tiles) must already be there: the input may arrive in pieces.
+cudaError_t rle_summary_range_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks_total, uint64_t c_first,
+                                     uint64_t c_last, uint64_t *d_lasthead, uint32_t *d_meta, uint32_t *d_restsum,
+                                     uint64_t *d_oin, uint64_t *d_P, uint64_t *d_tiles, cudaStream_t st)
+{
+    if (c_last <= c_first) return cudaSuccess;
+    if (c_first % rle::STILE) return cudaErrorInvalidValue;
+    unsigned grid = (unsigned)((c_last - c_first + rle::WPB - 1) / rle::WPB);
+    rle::rle_summary_kernel<<<grid, rle::WPB * 32, 0, st>>>(d_in, N, c_first, c_last, d_lasthead, d_meta, d_restsum);
+    const unsigned n_tiles_total = (unsigned)rle_scan_tiles(n_chunks_total);
+    const unsigned tile0 = (unsigned)(c_first / rle::STILE), tile1 = (unsigned)rle_scan_tiles(c_last);
+    uint64_t *tile_head = d_tiles, *tile_sum = d_tiles + n_tiles_total;
+    rle::rle_scan_heads_kernel<<<tile1 - tile0, rle::ST, 0, st>>>(d_lasthead, c_last, tile0, tile_head);
+    rle::rle_scan_oin_kernel<<<tile1 - tile0, rle::ST, 0, st>>>(d_lasthead, d_meta, d_restsum, c_last, tile0, tile_head,
+                                                                 d_oin, tile_sum);
+    rle::rle_scan_p_kernel<<<tile1 - tile0, rle::ST, 0, st>>>(d_meta, d_restsum, d_oin, c_last, tile0, tile1, tile_sum, d_P);
+    return cudaGetLastError();
+}
+
 cudaError_t rle_summary_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks, uint64_t *d_lasthead,
                                uint32_t *d_meta, uint32_t *d_restsum, uint64_t *d_oin, uint64_t *d_P,
                                uint64_t *d_tiles, cudaStream_t st)
 {
-    unsigned grid = (unsigned)((n_chunks + rle::WPB - 1) / rle::WPB);
-    rle::rle_summary_kernel<<<grid, rle::WPB * 32, 0, st>>>(d_in, N, n_chunks, d_lasthead, d_meta, d_restsum);
-    const unsigned n_tiles = (unsigned)rle_scan_tiles(n_chunks);
-    uint64_t *tile_head = d_tiles, *tile_sum = d_tiles + n_tiles;
-    rle::rle_scan_heads_kernel<<<n_tiles, rle::ST, 0, st>>>(d_lasthead, n_chunks, tile_head);
-    rle::rle_scan_oin_kernel<<<n_tiles, rle::ST, 0, st>>>(d_lasthead, d_meta, d_restsum, n_chunks, tile_head, d_oin, tile_sum);
-    rle::rle_scan_p_kernel<<<n_tiles, rle::ST, 0, st>>>(d_meta, d_restsum, d_oin, n_chunks, n_tiles, tile_sum, d_P);
-    return cudaGetLastError();
+    return rle_summary_range_launch(d_in, N, n_chunks, 0, n_chunks, d_lasthead, d_meta, d_restsum, d_oin, d_P, d_tiles, st);
 }
+
+uint64_t rle_scan_tile_chunks() { return rle::STILE; }
 
 size_t rle_scan_tiles(uint64_t n_chunks) { return (size_t)((n_chunks + rle::STILE - 1) / rle::STILE); }
 
