@@ -116,9 +116,9 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
 {
     if (!ctx) return;
     for (Device &d : ctx->devs) device_release(d);
-    if (ctx->aux) {
-        device_release(*ctx->aux);
-        delete ctx->aux;
+    for (Device *a : ctx->aux) {
+        device_release(*a);
+        delete a;
     }
     if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
     free(ctx->out_big);
@@ -150,6 +150,11 @@ extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
     if (!strcmp(key, "piece_blocks_per_sm_x16")) {
         if (value < 1 || value > 64) return BNZ_EINVAL;
         ctx->piece_blocks_per_sm_x16 = (int)value;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "h2d_pieces")) {
+        if (value < 2 || value > 8) return BNZ_EINVAL;
+        ctx->h2d_pieces = (int)value;
         return BNZ_OK;
     }
     if (!strcmp(key, "h2d_overlap")) {

@@ -229,13 +229,14 @@ static std::vector<uint32_t> split_blocks(const std::vector<RleBlock> &blocks, s
     return cut;
 }
 
-// One GPU, host input, many blocks: the input is uploaded and cut in two pieces.  The first piece
-// holds a little more than one block per CTA of the sort; its blocks are sorted (lane 0) while the
-// rest is still on the PCIe bus.  The chunk tables of the second piece continue the first's (the
-// scan carries are kept per tile), the host walk is simply repeated over the whole input (1 us per
-// block) and must reproduce the first piece's blocks; the remaining blocks run on a second lane of
-// the same device, whose sort CTAs take the SM slots the first launch frees.  *handled = false:
-// the input is too small for this, nothing was done.
+// One GPU, host input, many blocks: the input is uploaded and cut in pieces.  The first piece holds
+// about one block per SM; its blocks are sorted (lane 0) while the rest is still on the PCIe bus.
+// The chunk tables of a later piece continue the earlier ones (the scan carries are kept per tile),
+// the host walk is simply repeated over the input so far (1 us per block) and must reproduce the
+// earlier pieces' blocks; the new blocks run on a further lane of the same device, whose sort CTAs
+// take the SM slots the earlier launches leave and free.  A lane that finishes early runs its MTF,
+// Huffman and packing under the later lanes' sort.  *handled = false: the input is too small for
+// this, nothing was done.
 static int encode_pieces(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level, std::vector<Shard> &shards,
                          std::vector<uint32_t> &crcs, uint64_t *total_bits, uint64_t bit_base, bool *handled)
 {
@@ -244,32 +245,42 @@ static int encode_pieces(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level,
     const uint64_t n_chunks = (N + RLE_CHUNK - 1) / RLE_CHUNK;
     const uint64_t tile = rle_scan_tile_chunks();
     const uint64_t blk = (uint64_t)100000 * level;
-    // piece A: about one block per SM (rounded up to whole scan tiles).  Its sort CTAs then leave
-    // half of every SM free, so the RLE kernels of the second piece can run as soon as its bytes
+    // piece 0: about one block per SM (rounded up to whole scan tiles).  Its sort CTAs then leave
+    // half of every SM free, so the RLE kernels of the next piece can run as soon as its bytes
     // have arrived (behind a launch with two CTAs on every SM they waited ~25 ms for the first
     // blocks to finish), and one CTA per SM already sorts at 87 % of the rate of two.
     const uint64_t slots = (uint64_t)d0.sm_count * (uint64_t)ctx->piece_blocks_per_sm_x16 / 16;
-    uint64_t cA = ((slots * blk / RLE_CHUNK + tile - 1) / tile) * tile;
+    uint64_t c0 = ((slots * blk / RLE_CHUNK + tile - 1) / tile) * tile;
+    int K = ctx->h2d_pieces;
     if (ctx->h2d_overlap == 2) {                              // forced (tests): one scan tile, whatever the size
-        cA = tile;
-        if (cA * RLE_CHUNK * 2 > N) return BNZ_OK;
-    } else if (cA * RLE_CHUNK * 4 > N || N < ((size_t)256 << 20)) {
-        return BNZ_OK;                                        // too little to hide: the copy is short, two lanes cost latency
+        c0 = tile;
+        if (c0 * RLE_CHUNK * 2 > N) return BNZ_OK;
+    } else if (c0 * RLE_CHUNK * 4 > N || N < ((size_t)256 << 20)) {
+        return BNZ_OK;                                        // too little to hide: the copy is short, extra lanes cost latency
     }
-    const uint64_t bytesA = std::min<uint64_t>(N, cA * RLE_CHUNK + 4096);
-    if (!ctx->aux) {
-        ctx->aux = new Device();
-        if (!device_init(*ctx->aux, d0.id)) {
-            device_release(*ctx->aux);
-            delete ctx->aux;
-            ctx->aux = nullptr;
-            return fail(ctx, BNZ_ECUDA, "second lane");
+    // piece ends in chunks (multiples of the scan tile, the last one = n_chunks): the rest is split evenly
+    std::vector<uint64_t> cend;
+    cend.push_back(c0);
+    for (int k = 1; k < K; k++) {
+        uint64_t e = c0 + (n_chunks - c0) * (uint64_t)k / (uint64_t)(K - 1);
+        e = (k == K - 1) ? n_chunks : (e / tile) * tile;
+        if (e > cend.back()) cend.push_back(e);
+    }
+    if (cend.back() != n_chunks) cend.push_back(n_chunks);
+    K = (int)cend.size();
+    while ((int)ctx->aux.size() < K - 1) {
+        Device *a = new Device();
+        if (!device_init(*a, d0.id)) {
+            device_release(*a);
+            delete a;
+            return fail(ctx, BNZ_ECUDA, "extra lane");
         }
+        ctx->aux.push_back(a);
     }
-    Device &d1 = *ctx->aux;
+    auto lane = [&](int k) -> Device & { return k == 0 ? d0 : *ctx->aux[k - 1]; };
     *handled = true;
     bnz_stats &st = ctx->stats;
-    d0.launches = d1.launches = 0;
+    for (int k = 0; k < K; k++) lane(k).launches = 0;
     CK(ctx, cudaSetDevice(d0.id));
     CK(ctx, d0.in.ensure(N + 64));
     CK(ctx, d0.ch_lasthead.ensure(n_chunks * 8));
@@ -283,69 +294,68 @@ static int encode_pieces(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level,
     uint8_t *d_in = d0.in.as<uint8_t>();
     uint64_t *h_P = d0.h_P.as<uint64_t>(), *h_oin = d0.h_oin.as<uint64_t>();
 
-    // ---- piece A on lane 0; the copy of piece B is queued right behind it on lane 1's stream
-    CK(ctx, cudaEventRecord(d0.ev[0], d0.stream));
-    CK(ctx, cudaMemcpyAsync(d_in, h_in, bytesA, cudaMemcpyHostToDevice, d0.stream));
-    CK(ctx, cudaEventRecord(d0.ev[1], d0.stream));
-    CK(ctx, cudaEventRecord(d1.ev[0], d1.stream));
-    CK(ctx, cudaMemcpyAsync(d_in + bytesA, h_in + bytesA, N - bytesA, cudaMemcpyHostToDevice, d1.stream));
-    CK(ctx, cudaEventRecord(d1.ev[1], d1.stream));
-    st.h2d_bytes += N;
-    CK(ctx, rle_summary_range_launch(d_in, N, n_chunks, 0, cA, d0.ch_lasthead.as<uint64_t>(), d0.ch_meta.as<uint32_t>(),
-                                     d0.ch_restsum.as<uint32_t>(), d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(),
-                                     d0.ch_tiles.as<uint64_t>(), d0.stream));
-    d0.launches += 4;
-    CK(ctx, cudaMemcpyAsync(h_P, d0.ch_P.p, (cA + 1) * 8, cudaMemcpyDeviceToHost, d0.stream));
-    CK(ctx, cudaMemcpyAsync(h_oin, d0.ch_oin.p, cA * 8, cudaMemcpyDeviceToHost, d0.stream));
-    CK(ctx, cudaStreamSynchronize(d0.stream));
-    std::vector<RleBlock> blocksA;
-    uint64_t usedA = 0;
-    if (rle_walk_cuts(h_in, cA * RLE_CHUNK, level, h_P, h_oin, cA, blocksA, false, &usedA) != 0)
-        return fail(ctx, BNZ_EINTERNAL, "RLE1 cut walk failed");
-    CK(ctx, cudaEventRecord(d0.ev[8], d0.stream));
-
-    shards = std::vector<Shard>(2);
-    shards[0].d = &d0;
-    shards[1].d = &d1;
-    shards[0].blocks = blocksA;
-    std::thread tA([&]() {
-        t_err_sink = &shards[0].err;
-        shards[0].rc = blocksA.empty() ? BNZ_OK
-                                       : shard_model(ctx, shards[0], d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
-        t_err_sink = nullptr;
-    });
-
-    // ---- piece B: tables of the remaining chunks (lane 1's stream, behind its copy), whole walk
-    int rc = BNZ_OK;
-    auto pieceB = [&]() -> int {
-        CK(ctx, cudaSetDevice(d0.id));
-        CK(ctx, rle_summary_range_launch(d_in, N, n_chunks, cA, n_chunks, d0.ch_lasthead.as<uint64_t>(),
-                                         d0.ch_meta.as<uint32_t>(), d0.ch_restsum.as<uint32_t>(), d0.ch_oin.as<uint64_t>(),
-                                         d0.ch_P.as<uint64_t>(), d0.ch_tiles.as<uint64_t>(), d1.stream));
-        d1.launches += 4;
-        CK(ctx, cudaMemcpyAsync(h_P + cA, d0.ch_P.as<uint64_t>() + cA, (n_chunks + 1 - cA) * 8, cudaMemcpyDeviceToHost, d1.stream));
-        CK(ctx, cudaMemcpyAsync(h_oin + cA, d0.ch_oin.as<uint64_t>() + cA, (n_chunks - cA) * 8, cudaMemcpyDeviceToHost, d1.stream));
-        CK(ctx, cudaStreamSynchronize(d1.stream));
-        std::vector<RleBlock> all;
-        uint64_t used = 0;
-        if (rle_walk_cuts(h_in, N, level, h_P, h_oin, n_chunks, all, true, &used) != 0 || all.size() < blocksA.size())
-            return fail(ctx, BNZ_EINTERNAL, "RLE1 cut walk failed");
-        for (size_t b = 0; b < blocksA.size(); b++)
-            if (all[b].s != blocksA[b].s || all[b].c != blocksA[b].c || all[b].n != blocksA[b].n || all[b].rle_off != blocksA[b].rle_off)
-                return fail(ctx, BNZ_EINTERNAL, "cut chain of the first piece is not a prefix of the whole");
-        shards[1].blocks.assign(all.begin() + blocksA.size(), all.end());
-        if (shards[1].blocks.empty()) return BNZ_OK;
-        const uint64_t off0 = shards[1].blocks.front().rle_off;
-        for (RleBlock &b : shards[1].blocks) b.rle_off -= off0;
-        return shard_model(ctx, shards[1], d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
-    };
-    rc = pieceB();
-    tA.join();
-    if (shards[0].rc != BNZ_OK) {
-        ctx->err = shards[0].err;
-        return shards[0].rc;
+    // all copies are queued at once, each on its lane's stream (the copy engine takes them in order);
+    // a piece's bytes end one look-ahead page behind its last chunk
+    auto bytes_end = [&](int k) -> uint64_t { return k == K - 1 ? N : std::min<uint64_t>(N, cend[k] * RLE_CHUNK + 4096); };
+    for (int k = 0; k < K; k++) {
+        Device &d = lane(k);
+        const uint64_t a = k ? bytes_end(k - 1) : 0, b = bytes_end(k);
+        CK(ctx, cudaEventRecord(d.ev[0], d.stream));
+        CK(ctx, cudaMemcpyAsync(d_in + a, h_in + a, b - a, cudaMemcpyHostToDevice, d.stream));
+        CK(ctx, cudaEventRecord(d.ev[1], d.stream));
     }
+    st.h2d_bytes += N;
+
+    shards = std::vector<Shard>(K);
+    std::vector<std::thread> th;
+    std::vector<RleBlock> prev;                              // blocks cut so far
+    int rc = BNZ_OK;
+    for (int k = 0; k < K && rc == BNZ_OK; k++) {
+        Device &d = lane(k);
+        shards[k].d = &d;
+        const uint64_t ca = k ? cend[k - 1] : 0, cb = cend[k];
+        const bool last = k == K - 1;
+        auto plan = [&]() -> int {
+            CK(ctx, rle_summary_range_launch(d_in, N, n_chunks, ca, cb, d0.ch_lasthead.as<uint64_t>(),
+                                             d0.ch_meta.as<uint32_t>(), d0.ch_restsum.as<uint32_t>(), d0.ch_oin.as<uint64_t>(),
+                                             d0.ch_P.as<uint64_t>(), d0.ch_tiles.as<uint64_t>(), d.stream));
+            d.launches += 4;
+            CK(ctx, cudaMemcpyAsync(h_P + ca, d0.ch_P.as<uint64_t>() + ca, (cb + 1 - ca) * 8, cudaMemcpyDeviceToHost, d.stream));
+            CK(ctx, cudaMemcpyAsync(h_oin + ca, d0.ch_oin.as<uint64_t>() + ca, (cb - ca) * 8, cudaMemcpyDeviceToHost, d.stream));
+            CK(ctx, cudaStreamSynchronize(d.stream));
+            std::vector<RleBlock> all;
+            uint64_t used = 0;
+            if (rle_walk_cuts(h_in, last ? N : cb * RLE_CHUNK, level, h_P, h_oin, cb, all, last, &used) != 0 ||
+                all.size() < prev.size())
+                return fail(ctx, BNZ_EINTERNAL, "RLE1 cut walk failed");
+            for (size_t b = 0; b < prev.size(); b++)
+                if (all[b].s != prev[b].s || all[b].c != prev[b].c || all[b].n != prev[b].n || all[b].rle_off != prev[b].rle_off)
+                    return fail(ctx, BNZ_EINTERNAL, "cut chain of the earlier pieces is not a prefix of the longer one");
+            shards[k].blocks.assign(all.begin() + prev.size(), all.end());
+            prev.swap(all);
+            if (!shards[k].blocks.empty()) {
+                const uint64_t off0 = shards[k].blocks.front().rle_off;
+                for (RleBlock &b : shards[k].blocks) b.rle_off -= off0;
+            }
+            return BNZ_OK;
+        };
+        rc = plan();
+        if (rc != BNZ_OK) break;
+        th.emplace_back([&, k]() {
+            Shard &sh = shards[k];
+            t_err_sink = &sh.err;
+            sh.rc = sh.blocks.empty() ? BNZ_OK
+                                      : shard_model(ctx, sh, d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
+            t_err_sink = nullptr;
+        });
+    }
+    for (std::thread &t : th) t.join();
     if (rc != BNZ_OK) return rc;
+    for (Shard &sh : shards)
+        if (sh.rc != BNZ_OK) {
+            ctx->err = sh.err;
+            return sh.rc;
+        }
 
     uint64_t bits = bit_base;
     for (Shard &sh : shards) {
@@ -486,6 +496,8 @@ int pack_and_download(bnz_ctx *ctx, std::vector<Shard> &shards, uint8_t *o, bool
                       size_t o_first_byte)
 {
     std::vector<uint32_t> first_word(shards.size(), 0);
+    size_t first = 0;                                        // the first shard that holds blocks
+    while (first < shards.size() && shards[first].blocks.empty()) first++;
     for (size_t g = 0; g < shards.size(); g++) {
         Shard &sh = shards[g];
         if (sh.blocks.empty()) continue;
@@ -495,7 +507,7 @@ int pack_and_download(bnz_ctx *ctx, std::vector<Shard> &shards, uint8_t *o, bool
         int rc = shard_pack(ctx, sh, &bytes);
         if (rc != BNZ_OK) return rc;
         const size_t w0 = (size_t)(sh.bit_base >> 5) * 4 - o_first_byte;
-        if (g == 0 && stream_start) {
+        if (g == first && stream_start) {
             CK(ctx, cudaMemcpyAsync(o + w0, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
         } else {
             CK(ctx, cudaMemcpyAsync(&first_word[g], d.out.p, 4, cudaMemcpyDeviceToHost, d.stream));
@@ -512,7 +524,7 @@ int pack_and_download(bnz_ctx *ctx, std::vector<Shard> &shards, uint8_t *o, bool
     }
     // merge the words shared with the previous shard / batch
     for (size_t g = 0; g < shards.size(); g++) {
-        if (shards[g].blocks.empty() || (g == 0 && stream_start)) continue;
+        if (shards[g].blocks.empty() || (g == first && stream_start)) continue;
         uint8_t *w = o + ((size_t)(shards[g].bit_base >> 5) * 4 - o_first_byte);
         const uint8_t *f = reinterpret_cast<const uint8_t *>(&first_word[g]);
         if ((shards[g].bit_base & 31) == 0) memcpy(w, f, 4);

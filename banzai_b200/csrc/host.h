@@ -111,7 +111,8 @@ struct bnz_ctx {
     size_t max_batch_bytes = (size_t)3 << 30;   // inputs above this are encoded in streaming batches
     size_t stream_window_bytes = (size_t)512 << 20;   // bnz_stream_*: input bytes per pipeline window
     int open_streams = 0;
-    Device *aux = nullptr;             // second lane on the first device (created on demand): the blocks of a late-arriving input piece
+    std::vector<Device *> aux;         // further lanes on the first device (created on demand): the blocks of later input pieces
+    int h2d_pieces = 3;                // pieces the input of one call is uploaded in (first piece: see piece_blocks_per_sm_x16)
     int piece_blocks_per_sm_x16 = 17;  // size of the first piece in blocks per SM (x 1/16)
     int h2d_overlap = 1;               // one device, host input: upload in two pieces, sort the first while the second arrives
     int crc_low_prio = 1;              // block CRCs on the low-priority stream (they would delay the start of the sort)

@@ -59,8 +59,8 @@ BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
  *   "mtf_overlap"        percent of a device's blocks whose MTF may run beside the sort, in the SM
  *                        slots its tail leaves empty (70; 0 = strictly after the sort)
  *   "mtf_groups"         number of block lists the overlapped MTF is issued in (2)
- *   "h2d_overlap"        1 (default): one GPU, host input of >= 256 MiB: upload in two pieces and sort
- *                        the first while the second arrives | 0 single upload | 2 forced (tests)
+ *   "h2d_overlap"        1 (default): one GPU, host input of >= 256 MiB: upload in "h2d_pieces" (3)
+ *                        pieces and sort each while the next arrives | 0 single upload | 2 forced (tests)
  *   "crc_low_prio"       1: block CRCs on the low-priority stream (default) | 0: normal side stream
  *   "max_batch_bytes"    inputs above this (3 GiB) are encoded in batches so that device memory
  *                        stays bounded

@@ -8,7 +8,7 @@ n = 1 << 30
 data = corpus.mixed(n, seed=corpus.SEED_C2) if hasattr(corpus, "SEED_C2") else corpus.mixed(n)
 hp = _ffi.lib.bnz_host_alloc(n)
 C.memmove(hp, data.ctypes.data, n)
-for sets in ({"h2d_overlap": 0}, {"h2d_overlap": 1}, {"h2d_overlap": 1, "piece_blocks_per_sm_x16": 12}, {"h2d_overlap": 1, "piece_blocks_per_sm_x16": 24}, {"h2d_overlap": 1, "piece_blocks_per_sm_x16": 36}):
+for sets in ({"h2d_overlap": 0}, {"h2d_pieces": 2}, {"h2d_pieces": 3}, {"h2d_pieces": 4}, {"h2d_pieces": 6}):
     ctx = banzai_b200.Context(n_gpus=1)
     for k, v in sets.items(): ctx.set(k, v)
     best = 1e9
