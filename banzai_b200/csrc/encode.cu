@@ -344,8 +344,13 @@ static int encode_pieces(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level,
         th.emplace_back([&, k]() {
             Shard &sh = shards[k];
             t_err_sink = &sh.err;
-            sh.rc = sh.blocks.empty() ? BNZ_OK
-                                      : shard_model(ctx, sh, d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
+            if (cudaSetDevice(sh.d->id) != cudaSuccess) {            // a new thread starts on device 0
+                sh.err = "cudaSetDevice";
+                sh.rc = BNZ_ECUDA;
+            } else {
+                sh.rc = sh.blocks.empty() ? BNZ_OK
+                                          : shard_model(ctx, sh, d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
+            }
             t_err_sink = nullptr;
         });
     }

@@ -59,3 +59,20 @@ def test_streaming_front_end_on_two_devices():
         assert ctx.stats()["n_devices"] == 2
     assert sink.getvalue() == want
     assert bz2.decompress(want) == data
+
+
+@pytest.mark.skipif("_ngpu() < 2")
+def test_upload_in_pieces_on_a_device_other_than_0():
+    """the lanes of the piecewise upload run in their own host threads, which must select the
+    context's device (one process per GPU under torchrun: LOCAL_RANK > 0)"""
+    import banzai_b200
+    data = corpus.mixed(30 * 1000 * 1000 + 77)
+    want = O.encode(data, 1)
+    with banzai_b200.Context(devices=[1]) as ctx:
+        ctx.set("h2d_overlap", 2)
+        assert ctx.encode_bytes(data, 1) == want
+        import io
+        sink = io.BytesIO()
+        ctx.set("stream_window_bytes", 1 << 16)
+        assert ctx.encode_stream(io.BytesIO(data.tobytes()), sink, 1) == len(data)
+        assert sink.getvalue() == want
