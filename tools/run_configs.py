@@ -8,6 +8,7 @@ from oracle import pyoracle as O
 
 quick = len(sys.argv) > 1 and sys.argv[1] == 'quick'
 only_c5 = len(sys.argv) > 1 and sys.argv[1] == 'c5'
+only_big = len(sys.argv) > 1 and sys.argv[1] == 'big'     # C2, C4, C5 only (the cases too large for the test suite)
 ctx = banzai_b200.Context(n_gpus=1)
 
 def run(name, data, level, oracle_check, decode_check=True):
@@ -31,6 +32,11 @@ if only_c5:
     run("C5 random-4GiB-L9", corpus.random_bytes(4 << 30, corpus.SEED_C5), 9, False)
     sys.exit(0)
 # C1: 10 MB English-like text, level 9 (the CPU-runnable case; must be byte-identical)
+if only_big:
+    run("C2 mixed-1GiB", corpus.mixed(1 << 30, corpus.SEED_C2), 9, False)
+    run("C4 text-4GiB-L1", corpus.text(4 << 30, corpus.SEED_C4), 1, False)
+    run("C5 random-4GiB-L9", corpus.random_bytes(4 << 30, corpus.SEED_C5), 9, False)
+    sys.exit(0)
 run("C1 text-10MB", corpus.text(10 * 1000 * 1000, corpus.SEED_C1), 9, True)
 # C3: degenerate / periodic
 unit = corpus.random_bytes(1000, seed=corpus.SEED_C3).tobytes()
