@@ -17,17 +17,23 @@
 //   round 0   : key = S[i..i+5) (cyclic)                           -> sort -> rank_5
 //   round h   : key = (rank_h[i] : 20, rank_h[(i+h) mod n] : 20)   -> sort -> rank_2h
 //   only rotations whose rank is still shared ("active") are re-sorted; a rotation whose
-//   key became unique gets its final rank, its BWT byte is written at once
-//   (bwt[rank] = S[i-1]) and it drops out of later rounds.
+//   key became unique gets its final rank and drops out of later rounds.
 //   A round that splits no group proves the remaining groups are identical rotations
 //   (period | n); their positions inside the group are arbitrary for the BWT bytes and
 //   origPtr = group base + group size - 1.
+//   Last, one pass in index order writes bwt[rank[i]] = S[i-1] (coalesced reads, a one-byte
+//   scatter that covers the block's output at once and merges in L2).
 //
 // Radix pass (per tile of TILE records, sequential over tiles inside the CTA so that the
-// running bucket cursors live in shared memory): warp-striped coalesced load, per-warp
-// stable ranking with match.any, cross-warp scan, shared-memory reorder, coalesced
-// bucket-run stores.  The per-digit histograms of all passes are taken while the records
-// are generated, so each pass costs one read + one write of the records.
+// running bucket cursors live in shared memory): TMA bulk copy of the next tile while this one
+// is processed, per-warp stable ranking (one ballot per digit bit finds the lanes with the
+// same digit, one shared atomic with return value per digit group; counters are 16-bit pairs),
+// cross-warp scan, shared-memory reorder, coalesced bucket-run stores with an L2 evict_first
+// policy.  The per-digit histograms of all passes are taken while the records are generated
+// (in the then idle reorder buffer, parked in global memory during the passes), so each pass
+// costs one read + one write of the records.
+// DESIGN.md §4 has the measurements behind these choices (what bounds the kernel, what was
+// tried and dropped).
 #include "common.cuh"
 #include "kernels.h"
 
