@@ -212,3 +212,18 @@ def test_upload_in_pieces(level, size):
     with banzai_b200.Context(n_gpus=1) as c:
         c.set("h2d_overlap", 2)
         assert c.encode_bytes(zeros, 9) == O.encode(zeros, 9)
+
+
+def test_upload_in_pieces_automatic_mode():
+    """the automatic mode (>= 256 MiB and at least four first pieces' worth of input; here 300 MB
+    at level 3, three lanes) gives the bytes of the single-upload path"""
+    import banzai_b200
+    data = corpus.mixed(300 * 1000 * 1000)
+    with banzai_b200.Context(n_gpus=1) as c:
+        got = c.encode_bytes(data, 3)
+        assert c.stats()["n_devices"] == 3          # three lanes on the one GPU
+        c.set("h2d_overlap", 0)
+        plain = c.encode_bytes(data, 3)
+        assert c.stats()["n_devices"] == 1
+    assert got == plain
+    assert bz2.decompress(got) == data.tobytes()
