@@ -149,3 +149,14 @@ def test_encode_file_and_cli_pipe(tmp_path):
     p = subprocess.run([exe, "-c", "-"], input=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
     assert p.returncode == 0, p.stderr
     assert p.stdout == want
+
+
+def test_final_window_large_enough_for_the_piecewise_upload(ctx):
+    """a (final) window of >= 256 MiB takes the piecewise-upload path inside the stream's worker
+    thread; same bytes as the whole-buffer call"""
+    data = corpus.mixed(300 * 1000 * 1000).tobytes()
+    sink = io.BytesIO()
+    assert ctx.encode_stream(io.BytesIO(data), sink, 1) == len(data)
+    assert ctx.stats()["n_devices"] == 3
+    ctx.set("h2d_overlap", 0)
+    assert sink.getvalue() == ctx.encode_bytes(data, 1)
