@@ -70,6 +70,7 @@ void device_release(Device &d)
     d.h_acc.release();
     d.h_done.release();
     d.h_mtf.release();
+    d.h_tiles.release();
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.stream2) cudaStreamDestroy(d.stream2);
     for (cudaStream_t st : d.stream3)
@@ -160,6 +161,11 @@ extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
     if (!strcmp(key, "h2d_overlap")) {
         if (value < 0 || value > 2) return BNZ_EINVAL;
         ctx->h2d_overlap = (int)value;      // 0 off | 1 auto | 2 forced even for small inputs (tests)
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "reuse_input")) {
+        ctx->reuse_input = value != 0;
+        for (Device &d : ctx->devs) d.tag(nullptr, 0, 0, 0);
         return BNZ_OK;
     }
     if (!strcmp(key, "mtf_groups")) {

@@ -40,11 +40,6 @@ static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t
     CK(ctx, d.ptr.ensure((size_t)nb * 4));
     CK(ctx, d.has_byte.ensure((size_t)nb * 256));
     CK(ctx, d.bwt_stats.ensure((size_t)nb * sizeof(BwtStats)));
-    if (sh.bwt_after) {
-        while (sh.bwt_after->bwt_recorded.load(std::memory_order_acquire) == 0) std::this_thread::yield();
-        if (sh.bwt_after->bwt_recorded.load() > 0) CK(ctx, cudaStreamWaitEvent(d.stream, sh.bwt_after->d->ev[3], 0));
-        CK(ctx, cudaEventRecord(d.ev[2], d.stream));       // RLE stage ends where the sort may start
-    }
     // MTF arenas and the completion flags are set up before the sort is launched (allocation
     // would synchronise with it)
     rc = mtf_ensure(ctx, d, bt);
@@ -59,12 +54,8 @@ static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t
     rc = run_bwt_device(ctx, d, d.rle.as<uint8_t>(), d.bwt.as<uint8_t>(), d.blk_off.as<uint64_t>(),
                         d.blk_len.as<uint32_t>(), nb, bt.max_len, d.ptr.as<uint32_t>(), d.has_byte.as<uint8_t>(),
                         d.bwt_stats.as<BwtStats>(), ctx->mtf_overlap > 0 ? d_done : nullptr, &armed);
-    if (rc != BNZ_OK) {
-        sh.bwt_recorded.store(-1, std::memory_order_release);
-        return rc;
-    }
+    if (rc != BNZ_OK) return rc;
     CK(ctx, cudaEventRecord(d.ev[3], d.stream));
-    sh.bwt_recorded.store(1, std::memory_order_release);
 
     // K5 (the RLE1 images are dead once their block is sorted: their buffer holds the MTF index
     // bytes).  The one-CTA-per-block sort ends in a long tail (blocks differ 5x in cost and only
@@ -189,7 +180,9 @@ void finish_stats(bnz_ctx *ctx, std::vector<Shard> &shards, bool have_d2h)
     st.pack_ms += pack;
     st.d2h_ms += d2h;
     st.total_ms += total;
-    st.n_devices = std::max<uint32_t>(st.n_devices, (uint32_t)shards.size());
+    uint32_t busy = 0;
+    for (const Shard &sh : shards) busy += sh.blocks.empty() ? 0u : 1u;
+    st.n_devices = std::max<uint32_t>(st.n_devices, busy);
     st.bwt_radix_bits = (uint32_t)ctx->radix_bits;
 }
 
@@ -213,20 +206,223 @@ static int ensure_out_cache(bnz_ctx *ctx, size_t nbytes)
     return BNZ_OK;
 }
 
-// contiguous block ranges with ~equal RLE1 bytes per device
-static std::vector<uint32_t> split_blocks(const std::vector<RleBlock> &blocks, size_t n_dev)
-{
-    std::vector<uint32_t> cut(n_dev + 1, 0);
-    uint64_t total = 0;
-    for (const RleBlock &b : blocks) total += b.n;
-    uint64_t acc = 0;
-    size_t g = 1;
-    for (uint32_t i = 0; i < blocks.size() && g < n_dev; i++) {
-        acc += blocks[i].n;
-        while (g < n_dev && acc * n_dev >= total * g) cut[g++] = i + 1;
+// ---------------------------------------------------------------------------------------
+// Several devices, one stream (block independence: lib/lib.rs:101-126).
+// Every device uploads ONLY its own 1/G byte range and builds the chunk tables of that range; the
+// ranges are coupled by two scalars (the last run head before the range and the cost prefix at its
+// start), which the device threads exchange through host memory between the three table steps - no
+// collective, nothing is uploaded twice, no device waits for another one's bytes.  One thread then
+// walks the sequential cut chain over the stitched tables; a device owns the blocks that START in
+// its range and fetches the few bytes (and table entries) by which its last block reaches into
+// the next range.  From there on the devices are independent until the bit offsets are known.
+// ---------------------------------------------------------------------------------------
+namespace {
+struct HostBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    const int n;
+    int waiting = 0;
+    unsigned gen = 0;
+    explicit HostBarrier(int n_) : n(n_) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned g = gen;
+        if (++waiting == n) {
+            waiting = 0;
+            gen++;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return gen != g; });
+        }
     }
-    for (; g <= n_dev; g++) cut[g] = (uint32_t)blocks.size();
-    return cut;
+};
+}  // namespace
+
+static int encode_sharded(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level, std::vector<Shard> &shards,
+                          std::vector<uint32_t> &crcs, uint64_t *total_bits, bool final, uint64_t bit_base,
+                          uint64_t *consumed)
+{
+    bnz_stats &st = ctx->stats;
+    if (consumed) *consumed = 0;
+    const uint64_t n_chunks = (N + RLE_CHUNK - 1) / RLE_CHUNK;
+    const size_t G_all = ctx->devs.size();
+    const uint64_t per = (n_chunks + G_all - 1) / G_all;                 // chunks per device
+    const size_t G = (size_t)((n_chunks + per - 1) / per);               // devices that get a range
+    const uint64_t blk = (uint64_t)100000 * level;
+    const uint64_t slop = ((blk + blk / 4 + 4095) / 4096) * 4096;        // look-ahead uploaded with the range
+    const uint64_t max_reach = 51 * blk + 2 * RLE_CHUNK;                 // the longest input one block can swallow
+
+    Device &d0 = ctx->devs[0];
+    CK(ctx, cudaSetDevice(d0.id));
+    CK(ctx, d0.h_P.ensure((n_chunks + 1) * 8));                          // stitched tables (pinned, portable)
+    CK(ctx, d0.h_oin.ensure(n_chunks * 8));
+    uint64_t *h_P = d0.h_P.as<uint64_t>(), *h_oin = d0.h_oin.as<uint64_t>();
+
+    shards = std::vector<Shard>(G);
+    std::vector<uint64_t> head_max(G, 0), cost_sum(G, 0);
+    std::vector<RleBlock> all_blocks;
+    std::atomic<bool> abort_all{false};
+    int walk_rc = 0;
+    uint64_t used = 0;
+    HostBarrier bar((int)G);
+
+    auto work = [&](size_t g) -> int {
+        Shard &sh = shards[g];
+        Device &d = ctx->devs[g];
+        sh.d = &d;
+        d.launches = 0;
+        const uint64_t ca = g * per, cb = std::min(n_chunks, (g + 1) * per);
+        const uint64_t nt = (cb - ca + rle_scan_tile_chunks() - 1) / rle_scan_tile_chunks();
+        const uint64_t a = ca ? ca * RLE_CHUNK - 16 : 0;                 // first resident input byte
+        uint64_t b = std::min<uint64_t>(N, cb * RLE_CHUNK + slop);       // one past the last resident byte
+        const uint8_t *in_base = nullptr;
+        uint64_t *lasthead = nullptr, *oin = nullptr, *P = nullptr, *tile_head = nullptr, *tile_sum = nullptr;
+        uint32_t *meta = nullptr, *restsum = nullptr;
+        int rc = BNZ_OK;
+        bool resident = false;
+        uint64_t uploaded = 0;
+        auto step = [&](auto &&fn) {
+            if (rc == BNZ_OK && !abort_all.load()) {
+                rc = fn();
+                if (rc != BNZ_OK) abort_all.store(true);
+            }
+        };
+        // ---- own byte range -> device; chunk summaries and tile maxima
+        step([&]() -> int {
+            CK(ctx, cudaSetDevice(d.id));
+            const uint64_t reach = (cb - ca) + max_reach / RLE_CHUNK + 4;      // chunks the tables may have to cover
+            CK(ctx, d.in.ensure((cb * RLE_CHUNK - a) + max_reach + 4096));
+            CK(ctx, d.ch_lasthead.ensure((cb - ca) * 8));
+            CK(ctx, d.ch_meta.ensure((cb - ca) * 4));
+            CK(ctx, d.ch_restsum.ensure((cb - ca) * 4));
+            CK(ctx, d.ch_oin.ensure(reach * 8));
+            CK(ctx, d.ch_P.ensure((reach + 1) * 8));
+            CK(ctx, d.ch_tiles.ensure(nt * 16 + 64));
+            CK(ctx, d.h_tiles.ensure(nt * 16 + 64));
+            in_base = d.in.as<uint8_t>() - a;
+            lasthead = d.ch_lasthead.as<uint64_t>() - ca;
+            meta = d.ch_meta.as<uint32_t>() - ca;
+            restsum = d.ch_restsum.as<uint32_t>() - ca;
+            oin = d.ch_oin.as<uint64_t>() - ca;
+            P = d.ch_P.as<uint64_t>() - ca;
+            tile_head = d.ch_tiles.as<uint64_t>();
+            tile_sum = tile_head + nt;
+            CK(ctx, cudaEventRecord(d.ev[0], d.stream));
+            if (ctx->reuse_input && d.holds(h_in, N, a) && d.tag_b >= b) {
+                b = d.tag_b;                                          // resident since the previous call
+                resident = true;
+            } else {
+                CK(ctx, cudaMemcpyAsync(d.in.p, h_in + a, b - a, cudaMemcpyHostToDevice, d.stream));
+            }
+            CK(ctx, cudaEventRecord(d.ev[1], d.stream));
+            CK(ctx, rle_tables_heads_launch(in_base, N, ca, ca, cb, lasthead, meta, restsum, tile_head, d.stream));
+            CK(ctx, cudaMemcpyAsync(d.h_tiles.p, tile_head, nt * 8, cudaMemcpyDeviceToHost, d.stream));
+            CK(ctx, cudaStreamSynchronize(d.stream));
+            d.launches += 2;
+            for (uint64_t t = 0; t < nt; t++) head_max[g] = std::max(head_max[g], d.h_tiles.as<uint64_t>()[t]);
+            return BNZ_OK;
+        });
+        bar.wait();
+        // ---- run offsets at the chunk starts; tile cost sums
+        step([&]() -> int {
+            uint64_t carry_head = 0;
+            for (size_t q = 0; q < g; q++) carry_head = std::max(carry_head, head_max[q]);
+            CK(ctx, rle_tables_oin_launch(ca, ca, cb, carry_head, lasthead, meta, restsum, tile_head, oin, tile_sum, d.stream));
+            CK(ctx, cudaMemcpyAsync(d.h_tiles.p, tile_sum, nt * 8, cudaMemcpyDeviceToHost, d.stream));
+            CK(ctx, cudaStreamSynchronize(d.stream));
+            d.launches += 1;
+            for (uint64_t t = 0; t < nt; t++) cost_sum[g] += d.h_tiles.as<uint64_t>()[t];
+            return BNZ_OK;
+        });
+        bar.wait();
+        // ---- cost prefix; this range's slice of the stitched host tables
+        step([&]() -> int {
+            uint64_t carry_sum = 0;
+            for (size_t q = 0; q < g; q++) carry_sum += cost_sum[q];
+            CK(ctx, rle_tables_p_launch(ca, ca, cb, carry_sum, meta, restsum, oin, tile_sum, P, d.stream));
+            CK(ctx, cudaMemcpyAsync(h_P + ca, P + ca, (cb - ca + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
+            CK(ctx, cudaMemcpyAsync(h_oin + ca, oin + ca, (cb - ca) * 8, cudaMemcpyDeviceToHost, d.stream));
+            CK(ctx, cudaStreamSynchronize(d.stream));
+            d.launches += 1;
+            return BNZ_OK;
+        });
+        bar.wait();
+        // ---- the sequential cut chain, once; a device owns the blocks that start in its range
+        if (g == 0 && !abort_all.load()) {
+            walk_rc = rle_walk_cuts(h_in, N, level, h_P, h_oin, n_chunks, all_blocks, final, &used);
+            if (walk_rc == 0) {
+                size_t i = 0;
+                for (size_t q = 0; q < G; q++) {
+                    const uint64_t end = std::min<uint64_t>(N, (q + 1) * per * RLE_CHUNK);
+                    size_t j = i;
+                    while (j < all_blocks.size() && all_blocks[j].s < end) j++;
+                    shards[q].blocks.assign(all_blocks.begin() + i, all_blocks.begin() + j);
+                    const uint64_t off0 = (j > i) ? all_blocks[i].rle_off : 0;
+                    for (RleBlock &bk : shards[q].blocks) bk.rle_off -= off0;
+                    i = j;
+                }
+            } else {
+                abort_all.store(true);
+            }
+        }
+        bar.wait();
+        // ---- the part of the last block that reaches into the next range; then the block pipeline
+        step([&]() -> int {
+            if (sh.blocks.empty()) return BNZ_OK;
+            const uint64_t c_end = (sh.blocks.back().c + RLE_CHUNK - 1) / RLE_CHUNK;
+            const uint64_t e = std::min<uint64_t>(N, c_end * RLE_CHUNK + 16);
+            if (e - a > d.in.cap || c_end - ca + 1 > d.ch_P.cap / 8) return fail(ctx, BNZ_EINTERNAL, "block reaches beyond the reserved look-ahead");
+            if (e > b) {
+                CK(ctx, cudaMemcpyAsync(d.in.as<uint8_t>() + (b - a), h_in + b, e - b, cudaMemcpyHostToDevice, d.stream));
+                                b = e;
+            }
+            if (c_end > cb) {
+                CK(ctx, cudaMemcpyAsync(oin + cb, h_oin + cb, (c_end - cb) * 8, cudaMemcpyHostToDevice, d.stream));
+                CK(ctx, cudaMemcpyAsync(P + cb, h_P + cb, (c_end - cb + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+            }
+            return shard_model(ctx, sh, in_base, N, oin, P, level);
+        });
+        if (!resident) uploaded += std::min<uint64_t>(N, cb * RLE_CHUNK + slop) - a;
+        sh.h2d_bytes = uploaded;
+        if (ctx->reuse_input && rc == BNZ_OK) d.tag(h_in, N, a, b);
+        else d.tag(nullptr, 0, 0, 0);
+        return rc;
+    };
+
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++)
+        th.emplace_back([&, g]() {
+            t_err_sink = &shards[g].err;
+            shards[g].rc = work(g);
+            t_err_sink = nullptr;
+        });
+    for (std::thread &t : th) t.join();
+    if (walk_rc != 0) return fail(ctx, BNZ_EINTERNAL, "RLE1 cut walk failed");
+    for (Shard &sh : shards)
+        if (sh.rc != BNZ_OK) {
+            ctx->err = sh.err;
+            return sh.rc;
+        }
+    if (consumed) *consumed = used;
+    for (Shard &sh : shards) st.h2d_bytes += sh.h2d_bytes;
+    if (all_blocks.empty()) {           // (non-final batch shorter than one block)
+        shards.clear();
+        *total_bits = bit_base;
+        return BNZ_OK;
+    }
+
+    // bit offsets of the shards (blocks are concatenated at bit granularity, lib.rs:101-126 + out.rs)
+    uint64_t bits = bit_base;
+    for (Shard &sh : shards) {
+        sh.bit_base = bits;
+        bits += sh.block_bits;
+        crcs.insert(crcs.end(), sh.crcs.begin(), sh.crcs.end());
+    }
+    *total_bits = bits;
+    for (Shard &sh : shards)
+        if (!sh.blocks.empty()) add_stats(st, sh);
+    return BNZ_OK;
 }
 
 // One GPU, host input, many blocks: the input is uploaded and cut in pieces.  The first piece holds
@@ -305,6 +501,7 @@ static int encode_pieces(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level,
         CK(ctx, cudaEventRecord(d.ev[1], d.stream));
     }
     st.h2d_bytes += N;
+    if (ctx->reuse_input) d0.tag(h_in, N, 0, N);          // (the whole input ends up resident in d0.in)
 
     shards = std::vector<Shard>(K);
     std::vector<std::thread> th;
@@ -384,7 +581,8 @@ int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, size_t N
 {
     Device &d0 = ctx->devs[0];
     bnz_stats &st = ctx->stats;
-    if (ctx->h2d_overlap && ctx->devs.size() == 1 && !d_in0 && final && N >= ((size_t)16 << 20)) {
+    if (ctx->h2d_overlap && ctx->devs.size() == 1 && !d_in0 && final && N >= ((size_t)16 << 20) &&
+        !(ctx->reuse_input && d0.holds(h_in, N, 0) && d0.tag_b == N)) {
         bool handled = false;
         int rc = encode_pieces(ctx, h_in, N, level, shards, crcs, total_bits, bit_base, &handled);
         if (rc != BNZ_OK || handled) {
@@ -392,15 +590,23 @@ int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, size_t N
             return rc;
         }
     }
-    for (Device &d : ctx->devs) d.launches = 0;
+    if (ctx->devs.size() > 1) {
+        if (d_in0) return fail(ctx, BNZ_EINVAL, "device-resident input needs a single-GPU context");
+        int rc = encode_sharded(ctx, h_in, N, level, shards, crcs, total_bits, final, bit_base, consumed);
+        return rc;
+    }
+    d0.launches = 0;
     CK(ctx, cudaSetDevice(d0.id));
     CK(ctx, cudaEventRecord(d0.ev[0], d0.stream));
     const uint8_t *d_in = d_in0;
     if (!d_in) {
-        CK(ctx, d0.in.ensure(N + 64));
-        CK(ctx, cudaMemcpyAsync(d0.in.p, h_in, N, cudaMemcpyHostToDevice, d0.stream));
+        if (!(ctx->reuse_input && d0.holds(h_in, N, 0) && d0.tag_b == N)) {
+            CK(ctx, d0.in.ensure(N + 64));
+            CK(ctx, cudaMemcpyAsync(d0.in.p, h_in, N, cudaMemcpyHostToDevice, d0.stream));
+            st.h2d_bytes += N;
+            if (ctx->reuse_input) d0.tag(h_in, N, 0, N);
+        }
         d_in = d0.in.as<uint8_t>();
-        st.h2d_bytes += N;
     }
     CK(ctx, cudaEventRecord(d0.ev[1], d0.stream));
 
@@ -412,84 +618,16 @@ int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, size_t N
         *total_bits = bit_base;
         return BNZ_OK;
     }
-
-    CK(ctx, cudaEventRecord(d0.ev[8], d0.stream));       // input + chunk tables resident on device 0
-    const size_t n_dev = std::min(ctx->devs.size(), std::max<size_t>(1, blocks.size()));
-    std::vector<uint32_t> cut = split_blocks(blocks, n_dev);
-    shards = std::vector<Shard>(n_dev);
-    for (size_t g = 0; g < n_dev; g++) {
-        Shard &sh = shards[g];
-        sh.d = &ctx->devs[g];
-        if (g > 0 && ctx->devs[g].id == ctx->devs[g - 1].id) sh.bwt_after = &shards[g - 1];
-        sh.blocks.assign(blocks.begin() + cut[g], blocks.begin() + cut[g + 1]);
-        const uint64_t off0 = sh.blocks.empty() ? 0 : sh.blocks.front().rle_off;
-        for (RleBlock &b : sh.blocks) b.rle_off -= off0;
-    }
-
-    const uint64_t *h_P = d0.h_P.as<uint64_t>(), *h_oin = d0.h_oin.as<uint64_t>();
-    auto work = [&](size_t g) -> int {
-        Shard &sh = shards[g];
-        Device &d = *sh.d;
-        if (sh.blocks.empty()) {
-            sh.bwt_recorded.store(-1, std::memory_order_release);
-            return BNZ_OK;
-        }
-        CK(ctx, cudaSetDevice(d.id));
-        if (d.id == d0.id) {
-            // same physical GPU (lane 0, or an extra lane that overlaps its stages with the other
-            // lanes' kernels): the input and the chunk tables are already resident
-            if (g != 0) {
-                CK(ctx, cudaStreamWaitEvent(d.stream, d0.ev[8], 0));
-                CK(ctx, cudaEventRecord(d.ev[0], d.stream));
-                CK(ctx, cudaEventRecord(d.ev[1], d.stream));
-            }
-            return shard_model(ctx, sh, d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
-        }
-        // other devices: make their input range and chunk tables resident
-        CK(ctx, cudaEventRecord(d.ev[0], d.stream));
-        const uint64_t c0 = sh.blocks.front().s / RLE_CHUNK;
-        const uint64_t c1 = (sh.blocks.back().c + RLE_CHUNK - 1) / RLE_CHUNK;
-        const uint64_t a = c0 ? c0 * RLE_CHUNK - 16 : 0;
-        const uint64_t b = std::min<uint64_t>(N, c1 * RLE_CHUNK + 16);
-        CK(ctx, d.in.ensure(b - a + 64));
-        CK(ctx, cudaMemcpyAsync(d.in.p, h_in + a, b - a, cudaMemcpyHostToDevice, d.stream));
-        CK(ctx, d.ch_oin.ensure((c1 - c0 + 1) * 8));
-        CK(ctx, d.ch_P.ensure((c1 - c0 + 2) * 8));
-        CK(ctx, cudaMemcpyAsync(d.ch_oin.p, h_oin + c0, (c1 - c0) * 8, cudaMemcpyHostToDevice, d.stream));
-        CK(ctx, cudaMemcpyAsync(d.ch_P.p, h_P + c0, (c1 - c0 + 1) * 8, cudaMemcpyHostToDevice, d.stream));
-        CK(ctx, cudaEventRecord(d.ev[1], d.stream));
-        return shard_model(ctx, sh, d.in.as<uint8_t>() - a, N, d.ch_oin.as<uint64_t>() - c0, d.ch_P.as<uint64_t>() - c0, level);
-    };
-
-    if (n_dev == 1) {
-        rc = work(0);
-        if (rc != BNZ_OK) return rc;
-    } else {
-        std::vector<std::thread> th;
-        for (size_t g = 0; g < n_dev; g++)
-            th.emplace_back([&, g]() {
-                t_err_sink = &shards[g].err;
-                shards[g].rc = work(g);
-                if (shards[g].bwt_recorded.load() == 0) shards[g].bwt_recorded.store(-1, std::memory_order_release);
-                t_err_sink = nullptr;
-            });
-        for (std::thread &t : th) t.join();
-        for (Shard &sh : shards)
-            if (sh.rc != BNZ_OK) {
-                ctx->err = sh.err;
-                return sh.rc;
-            }
-    }
-
-    // bit offsets of the shards (blocks are concatenated at bit granularity, lib.rs:101-126 + out.rs)
-    uint64_t bits = bit_base;
-    for (Shard &sh : shards) {
-        sh.bit_base = bits;
-        bits += sh.block_bits;
-        crcs.insert(crcs.end(), sh.crcs.begin(), sh.crcs.end());
-    }
-    *total_bits = bits;
-    for (Shard &sh : shards) add_stats(st, sh);
+    shards = std::vector<Shard>(1);
+    Shard &sh = shards[0];
+    sh.d = &d0;
+    sh.blocks.swap(blocks);
+    rc = shard_model(ctx, sh, d_in, N, d0.ch_oin.as<uint64_t>(), d0.ch_P.as<uint64_t>(), level);
+    if (rc != BNZ_OK) return rc;
+    sh.bit_base = bit_base;
+    *total_bits = bit_base + sh.block_bits;
+    crcs.insert(crcs.end(), sh.crcs.begin(), sh.crcs.end());
+    add_stats(st, sh);
     return BNZ_OK;
 }
 

@@ -85,9 +85,15 @@ struct Device {
     DevBuf lens, codes, tf, num_tables, num_sel, span_base, hdr, hdr_bits, crc, blk_bits, blk_bitoff,
         total_bits, out;
     cudaEvent_t ev[16] = {};
-    PinBuf h_P, h_oin, h_acc, h_mtf, h_done;   // h_done: per-block completion flags the sort writes (mapped)
+    PinBuf h_P, h_oin, h_acc, h_mtf, h_done, h_tiles;   // h_done: per-block completion flags the sort writes (mapped)
     bool crc_tables = false;
     uint32_t launches = 0;
+    // what d.in holds (ctx->reuse_input): bytes [tag_a, tag_b) of the host buffer tag_ptr[0, tag_len)
+    const void *tag_ptr = nullptr;
+    size_t tag_len = 0;
+    uint64_t tag_a = 0, tag_b = 0;
+    bool holds(const void *p, size_t n, uint64_t a) const { return tag_ptr && tag_ptr == p && tag_len == n && tag_a == a; }
+    void tag(const void *p, size_t n, uint64_t a, uint64_t b) { tag_ptr = p; tag_len = n; tag_a = a; tag_b = b; }
 };
 
 struct bnz_ctx {
@@ -116,6 +122,7 @@ struct bnz_ctx {
     int piece_blocks_per_sm_x16 = 17;  // size of the first piece in blocks per SM (x 1/16)
     int h2d_overlap = 1;               // one device, host input: upload in two pieces, sort the first while the second arrives
     int crc_low_prio = 1;              // block CRCs on the low-priority stream (they would delay the start of the sort)
+    int reuse_input = 0;               // the caller re-encodes the SAME host buffer: keep its device copy resident (benchmarks)
     int mtf_groups = 2;
     int mtf_overlap = 70;              // percent of a device's blocks whose MTF may run beside the sort (0: off)
 };
@@ -207,10 +214,7 @@ struct Shard {
     uint64_t bit_base = 0;             // global bit offset of the shard's first block
     int rc = BNZ_OK;
     std::string err;
-    // lanes on one GPU: the persistent BWT kernels must not share the SMs, so lane g's sort waits
-    // for lane g-1's (event recorded on that lane's stream; the flag orders the host threads)
-    Shard *bwt_after = nullptr;
-    std::atomic<int> bwt_recorded{0};
+    uint64_t h2d_bytes = 0;            // input bytes this shard's device received
     Shard() = default;
     Shard(const Shard &o) { d = o.d; }
 };

@@ -35,6 +35,15 @@ uint64_t rle_scan_tile_chunks();
 cudaError_t rle_summary_range_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks_total, uint64_t c_first,
                                      uint64_t c_last, uint64_t *d_lasthead, uint32_t *d_meta, uint32_t *d_restsum,
                                      uint64_t *d_oin, uint64_t *d_P, uint64_t *d_tiles, cudaStream_t st);
+cudaError_t rle_tables_heads_launch(const uint8_t *d_in, uint64_t N, uint64_t c_base, uint64_t c_first, uint64_t c_last,
+                                    uint64_t *d_lasthead, uint32_t *d_meta, uint32_t *d_restsum, uint64_t *d_tile_head,
+                                    cudaStream_t st);
+cudaError_t rle_tables_oin_launch(uint64_t c_base, uint64_t c_first, uint64_t c_last, uint64_t carry_head,
+                                  const uint64_t *d_lasthead, const uint32_t *d_meta, const uint32_t *d_restsum,
+                                  const uint64_t *d_tile_head, uint64_t *d_oin, uint64_t *d_tile_sum, cudaStream_t st);
+cudaError_t rle_tables_p_launch(uint64_t c_base, uint64_t c_first, uint64_t c_last, uint64_t carry_sum,
+                                const uint32_t *d_meta, const uint32_t *d_restsum, const uint64_t *d_oin,
+                                const uint64_t *d_tile_sum, uint64_t *d_P, cudaStream_t st);
 cudaError_t rle_summary_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks, uint64_t *d_lasthead,
                                uint32_t *d_meta, uint32_t *d_restsum, uint64_t *d_oin, uint64_t *d_P,
                                uint64_t *d_tiles /* 2 * rle_scan_tiles(n_chunks) words of scratch */,

@@ -196,12 +196,14 @@ __device__ __forceinline__ u64 block_excl_sum64(u64 v, u64 *sh, u64 *total)
 // run head so far -> run offset o_in at every chunk start), then a running sum of the chunk costs
 // (-> P).  One CTA per tile of STILE chunks, three launches: tile maxima; o_in + tile cost sums
 // (the carry is the maximum over the earlier tiles, at most a few hundred values); P.
-__global__ void __launch_bounds__(ST) rle_scan_heads_kernel(const u64 *__restrict__ lasthead, u64 n_chunks, u32 tile0,
-                                                           u64 *__restrict__ tile_head)
+// Tile t covers the chunks [c_base + t * STILE, c_base + (t + 1) * STILE): c_base is the first chunk
+// of the range this device owns (0 on a single device), so ranges need no tile alignment.
+__global__ void __launch_bounds__(ST) rle_scan_heads_kernel(const u64 *__restrict__ lasthead, u64 n_chunks, u64 c_base,
+                                                           u32 tile0, u64 *__restrict__ tile_head)
 {
     __shared__ u64 sh[40];
     const u32 tile = tile0 + blockIdx.x;
-    const u64 c0 = (u64)tile * STILE + (u64)threadIdx.x * SI;
+    const u64 c0 = c_base + (u64)tile * STILE + (u64)threadIdx.x * SI;
     u64 agg = 0;
 #pragma unroll
     for (int k = 0; k < SI; k++)
@@ -221,20 +223,20 @@ __device__ __forceinline__ u64 chunk_cost(u32 mt, u32 rs, u64 oin)
 }
 
 __global__ void __launch_bounds__(ST) rle_scan_oin_kernel(const u64 *__restrict__ lasthead, const u32 *__restrict__ meta,
-                                                         const u32 *__restrict__ restsum, u64 n_chunks, u32 tile0,
-                                                         const u64 *__restrict__ tile_head, u64 *__restrict__ o_in,
-                                                         u64 *__restrict__ tile_sum)
+                                                         const u32 *__restrict__ restsum, u64 n_chunks, u64 c_base,
+                                                         u32 tile0, u64 carry_in, const u64 *__restrict__ tile_head,
+                                                         u64 *__restrict__ o_in, u64 *__restrict__ tile_sum)
 {
     __shared__ u64 sh[40];
     const u32 t = tile0 + blockIdx.x;
     u64 tot;
-    // carry: last run head in the earlier tiles
-    u64 cm = 0;
+    // carry: last run head in the earlier tiles (carry_in: in the ranges of the devices before this one)
+    u64 cm = carry_in;
     for (u32 q = threadIdx.x; q < t; q += ST) cm = max(cm, tile_head[q]);
     block_excl_max64(cm, sh, &tot);
     const u64 carry_head = tot;
 
-    const u64 c0 = (u64)t * STILE + (u64)threadIdx.x * SI;
+    const u64 c0 = c_base + (u64)t * STILE + (u64)threadIdx.x * SI;
     u64 lh[SI];
     u64 agg = 0;
 #pragma unroll
@@ -260,9 +262,9 @@ __global__ void __launch_bounds__(ST) rle_scan_oin_kernel(const u64 *__restrict_
 }
 
 __global__ void __launch_bounds__(ST) rle_scan_p_kernel(const u32 *__restrict__ meta, const u32 *__restrict__ restsum,
-                                                       const u64 *__restrict__ o_in, u64 n_chunks, u32 tile0,
-                                                       u32 n_tiles, const u64 *__restrict__ tile_sum,
-                                                       u64 *__restrict__ P)
+                                                       const u64 *__restrict__ o_in, u64 n_chunks, u64 c_base,
+                                                       u32 tile0, u32 n_tiles, u64 carry_in,
+                                                       const u64 *__restrict__ tile_sum, u64 *__restrict__ P)
 {
     __shared__ u64 sh[40];
     const u32 t = tile0 + blockIdx.x;
@@ -270,9 +272,9 @@ __global__ void __launch_bounds__(ST) rle_scan_p_kernel(const u32 *__restrict__ 
     u64 cs = 0;
     for (u32 q = threadIdx.x; q < t; q += ST) cs += tile_sum[q];
     block_excl_sum64(cs, sh, &tot);
-    const u64 carry_sum = tot;
+    const u64 carry_sum = tot + carry_in;           // carry_in = P at c_base (cost of the earlier devices' ranges)
 
-    const u64 c0 = (u64)t * STILE + (u64)threadIdx.x * SI;
+    const u64 c0 = c_base + (u64)t * STILE + (u64)threadIdx.x * SI;
     u64 sv[SI];
     u64 tsum = 0;
 #pragma unroll
@@ -590,25 +592,66 @@ uint32_t crc_finalize(uint32_t acc, uint64_t len)
     return acc ^ rle::gf_mul(0xFFFFFFFFu, p) ^ 0xFFFFFFFFu;
 }
 
-// chunk tables for chunks [c_first, c_last) of an input of n_chunks_total chunks; c_first must be
-// a multiple of the scan tile (rle_scan_tile_chunks()).  The tables of the chunks before c_first
-// (and their tile aggregates in d_tiles) must already be there: the input may arrive in pieces.
+// The chunk tables in three steps, so that several devices can each build the tables of their own
+// chunk range [c_base, ...) and exchange two scalars in between (encode.cu, encode_sharded):
+//   heads: chunk summaries + per-tile maximum of the last run head      -> tile_head[]
+//   oin  : run offset at every chunk start + per-tile cost sums          -> o_in[], tile_sum[]
+//          (carry_head = last run head, 1-based global position, before chunk c_base; 0 = none)
+//   p    : cost prefix                                                   -> P[], P[c_last]
+//          (carry_sum = P at chunk c_base)
+// Chunks [c_first, c_last) are processed; (c_first - c_base) must be a multiple of the scan tile and
+// the tables / tile aggregates of [c_base, c_first) must already be there (input arriving in pieces).
+// All table pointers are indexed by GLOBAL chunk number (the caller rebases them).
+static inline unsigned tiles_upto(uint64_t c_base, uint64_t c) { return (unsigned)((c - c_base + rle::STILE - 1) / rle::STILE); }
+
+cudaError_t rle_tables_heads_launch(const uint8_t *d_in, uint64_t N, uint64_t c_base, uint64_t c_first, uint64_t c_last,
+                                    uint64_t *d_lasthead, uint32_t *d_meta, uint32_t *d_restsum, uint64_t *d_tile_head,
+                                    cudaStream_t st)
+{
+    if (c_last <= c_first) return cudaSuccess;
+    if ((c_first - c_base) % rle::STILE) return cudaErrorInvalidValue;
+    unsigned grid = (unsigned)((c_last - c_first + rle::WPB - 1) / rle::WPB);
+    rle::rle_summary_kernel<<<grid, rle::WPB * 32, 0, st>>>(d_in, N, c_first, c_last, d_lasthead, d_meta, d_restsum);
+    const unsigned tile0 = tiles_upto(c_base, c_first), tile1 = tiles_upto(c_base, c_last);
+    rle::rle_scan_heads_kernel<<<tile1 - tile0, rle::ST, 0, st>>>(d_lasthead, c_last, c_base, tile0, d_tile_head);
+    return cudaGetLastError();
+}
+
+cudaError_t rle_tables_oin_launch(uint64_t c_base, uint64_t c_first, uint64_t c_last, uint64_t carry_head,
+                                  const uint64_t *d_lasthead, const uint32_t *d_meta, const uint32_t *d_restsum,
+                                  const uint64_t *d_tile_head, uint64_t *d_oin, uint64_t *d_tile_sum, cudaStream_t st)
+{
+    if (c_last <= c_first) return cudaSuccess;
+    const unsigned tile0 = tiles_upto(c_base, c_first), tile1 = tiles_upto(c_base, c_last);
+    rle::rle_scan_oin_kernel<<<tile1 - tile0, rle::ST, 0, st>>>(d_lasthead, d_meta, d_restsum, c_last, c_base, tile0, carry_head,
+                                                                 d_tile_head, d_oin, d_tile_sum);
+    return cudaGetLastError();
+}
+
+cudaError_t rle_tables_p_launch(uint64_t c_base, uint64_t c_first, uint64_t c_last, uint64_t carry_sum,
+                                const uint32_t *d_meta, const uint32_t *d_restsum, const uint64_t *d_oin,
+                                const uint64_t *d_tile_sum, uint64_t *d_P, cudaStream_t st)
+{
+    if (c_last <= c_first) return cudaSuccess;
+    const unsigned tile0 = tiles_upto(c_base, c_first), tile1 = tiles_upto(c_base, c_last);
+    rle::rle_scan_p_kernel<<<tile1 - tile0, rle::ST, 0, st>>>(d_meta, d_restsum, d_oin, c_last, c_base, tile0, tile1, carry_sum,
+                                                               d_tile_sum, d_P);
+    return cudaGetLastError();
+}
+
+// all three steps on one device (c_base = 0, no carries)
 cudaError_t rle_summary_range_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks_total, uint64_t c_first,
                                      uint64_t c_last, uint64_t *d_lasthead, uint32_t *d_meta, uint32_t *d_restsum,
                                      uint64_t *d_oin, uint64_t *d_P, uint64_t *d_tiles, cudaStream_t st)
 {
     if (c_last <= c_first) return cudaSuccess;
-    if (c_first % rle::STILE) return cudaErrorInvalidValue;
-    unsigned grid = (unsigned)((c_last - c_first + rle::WPB - 1) / rle::WPB);
-    rle::rle_summary_kernel<<<grid, rle::WPB * 32, 0, st>>>(d_in, N, c_first, c_last, d_lasthead, d_meta, d_restsum);
     const unsigned n_tiles_total = (unsigned)rle_scan_tiles(n_chunks_total);
-    const unsigned tile0 = (unsigned)(c_first / rle::STILE), tile1 = (unsigned)rle_scan_tiles(c_last);
     uint64_t *tile_head = d_tiles, *tile_sum = d_tiles + n_tiles_total;
-    rle::rle_scan_heads_kernel<<<tile1 - tile0, rle::ST, 0, st>>>(d_lasthead, c_last, tile0, tile_head);
-    rle::rle_scan_oin_kernel<<<tile1 - tile0, rle::ST, 0, st>>>(d_lasthead, d_meta, d_restsum, c_last, tile0, tile_head,
-                                                                 d_oin, tile_sum);
-    rle::rle_scan_p_kernel<<<tile1 - tile0, rle::ST, 0, st>>>(d_meta, d_restsum, d_oin, c_last, tile0, tile1, tile_sum, d_P);
-    return cudaGetLastError();
+    cudaError_t e = rle_tables_heads_launch(d_in, N, 0, c_first, c_last, d_lasthead, d_meta, d_restsum, tile_head, st);
+    if (e != cudaSuccess) return e;
+    e = rle_tables_oin_launch(0, c_first, c_last, 0, d_lasthead, d_meta, d_restsum, tile_head, d_oin, tile_sum, st);
+    if (e != cudaSuccess) return e;
+    return rle_tables_p_launch(0, c_first, c_last, 0, d_meta, d_restsum, d_oin, tile_sum, d_P, st);
 }
 
 cudaError_t rle_summary_launch(const uint8_t *d_in, uint64_t N, uint64_t n_chunks, uint64_t *d_lasthead,

@@ -1,6 +1,7 @@
-"""Host-side helpers for one-process-per-GPU launches (torchrun): the block-compression path
-shards by independent objects, so ranks never exchange data — only a timing barrier and a
-max-over-ranks reduction (NCCL on GPUs, gloo in the CPU tests)."""
+"""Host-side helpers for one-process-per-GPU launches (torchrun).  The block-compression path has
+no data-path collective: one stream is sharded over the GPUs by the process that owns the stream
+(bnz_ctx_create(n_gpus=N)), independent objects are encoded by independent ranks.  Ranks share
+only a timing barrier and a max-over-ranks reduction (NCCL on GPUs, gloo in the CPU tests)."""
 import os
 
 
@@ -56,6 +57,25 @@ class Group:
     def close(self):
         if self.dist is not None and self.dist.is_initialized():
             self.dist.destroy_process_group()
+
+
+class CpuGate:
+    """A barrier the waiting ranks sit in on the CPU (gloo).  While rank 0 drives every GPU of the
+    box for the one-stream measurement the other ranks must not wait inside an NCCL barrier: its
+    kernel would spin on the very SMs being measured."""
+
+    def __init__(self, group):
+        self.dist = group.dist
+        self.pg = None
+        if self.dist is not None:
+            self.pg = self.dist.new_group(backend="gloo")
+
+    def wait(self):
+        if self.pg is not None:
+            self.dist.barrier(group=self.pg)
+
+    def close(self):
+        self.pg = None
 
 
 def aggregate_throughput(bytes_per_rank, world, elapsed_max_s, steps):

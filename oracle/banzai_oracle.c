@@ -1231,4 +1231,171 @@ ORC_API int orc_encode(const uint8_t *in, size_t n, int level, uint8_t **out, si
     return orc_encode_ex(in, n, level, out, out_len, consumed_out, NULL, 0, NULL);
 }
 
+/* ------------------------------------------------------------------------ */
+/* Block-parallel driver of the SAME restatement (not in the reference: banzai is
+ * single-threaded).  The calling thread walks the sequential cut chain (lib.rs:102,
+ * 122-125: block k+1 starts where rle_one stopped) and hands every block to a pool of
+ * worker threads; a worker runs rle_one/bwt/mtf/huffman of its block into a private
+ * bit writer (lib.rs:110-117 read nothing but the block's own data); the blocks'
+ * bit strings are then appended in order through the reference's bit writer, which
+ * is exactly what the sequential loop would have written.  Used to pin parity at the
+ * benchmark's full sizes and as the all-cores CPU arm of bench.py.               */
+/* ------------------------------------------------------------------------ */
+#include <pthread.h>
+
+typedef struct {
+    size_t in_off;
+    uint8_t *bits;          /* whole bytes of the block's bit string */
+    size_t len;             /* number of whole bytes                  */
+    uint8_t strand;         /* trailing partial byte (MSB aligned)    */
+    size_t strand_bits;
+    uint32_t crc;
+    int done;
+} MtBlock;
+
+typedef struct {
+    const uint8_t *in;
+    size_t n;
+    int level;
+    MtBlock *blocks;        /* grown by the producer under the lock */
+    size_t n_blocks, cap_blocks;
+    size_t next;            /* next block a worker may take */
+    int producer_done;
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+} MtJob;
+
+static void mt_encode_block(const MtJob *job, size_t in_off, MtBlock *res, uint8_t *rle_buf, uint8_t *bwt_buf,
+                            uint16_t *mtf_buf, uint8_t *selectors)
+{
+    size_t rle_len = 0, took = 0;
+    uint32_t chk = 0;
+    orc_rle_one(job->in + in_off, job->n - in_off, job->level, rle_buf, &rle_len, &took, &chk);
+    uint32_t ptr = 0;
+    uint8_t has_byte[256];
+    orc_bwt(rle_buf, rle_len, bwt_buf, &ptr, has_byte);
+    BitWriter w;
+    bw_init(&w);
+    write_block_header(&w, chk, ptr);
+    write_sym_map(&w, has_byte);
+    size_t m = 0, num_syms = 0;
+    uint64_t freqs[258];
+    orc_mtf_and_rle(bwt_buf, rle_len, has_byte, mtf_buf, &m, &num_syms, freqs);
+    uint8_t tables[MAX_TABLES][MAX_SYMS];
+    memset(tables, 0, sizeof tables);
+    size_t nt = 0, ns = 0;
+    huffman_model(mtf_buf, m, num_syms, freqs, &nt, tables, selectors, &ns);
+    huffman_write(&w, mtf_buf, m, num_syms, nt, tables, selectors, ns);
+    res->bits = w.buf;
+    res->len = w.len;
+    res->strand = w.strand;
+    res->strand_bits = w.strand_bits;
+    res->crc = chk;
+}
+
+static void *mt_worker(void *arg)
+{
+    MtJob *job = (MtJob *)arg;
+    size_t cap = (size_t)100000 * (size_t)job->level;
+    uint8_t *rle_buf = (uint8_t *)xmalloc(cap);
+    uint8_t *bwt_buf = (uint8_t *)xmalloc(cap);
+    uint16_t *mtf_buf = (uint16_t *)xmalloc((cap + 1) * sizeof(uint16_t));
+    uint8_t *selectors = (uint8_t *)xmalloc(cap / SEGMENT_WIDTH + 2);
+    for (;;) {
+        pthread_mutex_lock(&job->mu);
+        while (job->next >= job->n_blocks && !job->producer_done) pthread_cond_wait(&job->cv, &job->mu);
+        if (job->next >= job->n_blocks) {
+            pthread_mutex_unlock(&job->mu);
+            break;
+        }
+        size_t k = job->next++;
+        size_t in_off = job->blocks[k].in_off;
+        pthread_mutex_unlock(&job->mu);
+        MtBlock res;
+        memset(&res, 0, sizeof res);
+        mt_encode_block(job, in_off, &res, rle_buf, bwt_buf, mtf_buf, selectors);
+        pthread_mutex_lock(&job->mu);               /* blocks[] may have been re-allocated meanwhile */
+        res.in_off = in_off;
+        res.done = 1;
+        job->blocks[k] = res;
+        pthread_mutex_unlock(&job->mu);
+    }
+    free(rle_buf);
+    free(bwt_buf);
+    free(mtf_buf);
+    free(selectors);
+    return NULL;
+}
+
+ORC_API int orc_encode_mt(const uint8_t *in, size_t n, int level, int threads, uint8_t **out, size_t *out_len,
+                          size_t *n_blocks_out)
+{
+    if (level < 1 || level > 9) return -1;
+    if (threads < 1) threads = 1;
+    MtJob job;
+    memset(&job, 0, sizeof job);
+    job.in = in;
+    job.n = n;
+    job.level = level;
+    job.cap_blocks = 1024;
+    job.blocks = (MtBlock *)xmalloc(job.cap_blocks * sizeof(MtBlock));
+    pthread_mutex_init(&job.mu, NULL);
+    pthread_cond_init(&job.cv, NULL);
+    pthread_t *th = (pthread_t *)xmalloc((size_t)threads * sizeof(pthread_t));
+    for (int t = 0; t < threads; t++)
+        if (pthread_create(&th[t], NULL, mt_worker, &job) != 0) orc_panic("pthread_create");
+
+    /* the sequential cut chain (lib.rs:101-126 without the per-block work) */
+    size_t cap = (size_t)100000 * (size_t)level;
+    uint8_t *rle_buf = (uint8_t *)xmalloc(cap);
+    size_t consumed = 0;
+    while (consumed < n) {
+        size_t rle_len = 0, took = 0;
+        orc_rle_one(in + consumed, n - consumed, level, rle_buf, &rle_len, &took, NULL);
+        if (took == 0) break;
+        pthread_mutex_lock(&job.mu);
+        if (job.n_blocks == job.cap_blocks) {
+            job.cap_blocks *= 2;
+            job.blocks = (MtBlock *)realloc(job.blocks, job.cap_blocks * sizeof(MtBlock));
+            if (!job.blocks) orc_panic("out of memory");
+        }
+        memset(&job.blocks[job.n_blocks], 0, sizeof(MtBlock));
+        job.blocks[job.n_blocks].in_off = consumed;
+        job.n_blocks++;
+        pthread_cond_signal(&job.cv);
+        pthread_mutex_unlock(&job.mu);
+        consumed += took;
+    }
+    free(rle_buf);
+    pthread_mutex_lock(&job.mu);
+    job.producer_done = 1;
+    pthread_cond_broadcast(&job.cv);
+    pthread_mutex_unlock(&job.mu);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(th);
+
+    /* stitch: exactly the writes of the sequential loop, in order */
+    BitWriter w;
+    bw_init(&w);
+    write_stream_header(&w, level);
+    uint32_t stream_crc = 0;
+    for (size_t k = 0; k < job.n_blocks; k++) {
+        MtBlock *b = &job.blocks[k];
+        if (!b->done) orc_panic("block not encoded");
+        stream_crc = b->crc ^ ((stream_crc << 1) | (stream_crc >> 31));   /* lib.rs:108 */
+        bw_write_bytes(&w, b->bits, b->len);
+        if (b->strand_bits) bw_write_bits(&w, (uint8_t)(b->strand >> (8 - b->strand_bits)), b->strand_bits);
+        free(b->bits);
+    }
+    write_stream_footer(&w, stream_crc);
+    bw_close(&w);
+    if (n_blocks_out) *n_blocks_out = job.n_blocks;
+    free(job.blocks);
+    pthread_mutex_destroy(&job.mu);
+    pthread_cond_destroy(&job.cv);
+    *out = w.buf;
+    *out_len = w.len;
+    return 0;
+}
+
 ORC_API void orc_free(void *p) { free(p); }

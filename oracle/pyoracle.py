@@ -57,6 +57,8 @@ def lib():
                                          C.c_void_p, C.c_size_t]
         L.orc_encode_ex.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), szp,
                                     szp, C.c_void_p, C.c_size_t, szp]
+        L.orc_encode_mt.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                    szp, szp]
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_bw_new.restype = C.c_void_p
         L.orc_bw_write_bits.argtypes = [C.c_void_p, C.c_uint32, C.c_size_t]
@@ -190,6 +192,29 @@ def encode(data, level, with_info=False):
         assert nb.value <= cap
         return res, [infos[i] for i in range(nb.value)]
     return res
+
+
+def encode_mt(data, level, threads=0, digest=False):
+    """The same restatement with one worker thread per block (orc_encode_mt): sequential cut
+    chain, blocks encoded in parallel, bit strings appended in order.  Byte-identical to
+    encode(); affordable at the benchmark's full sizes.  threads=0: all host cores.
+    digest=True returns (sha256 hex, length, n_blocks) without copying the stream into Python."""
+    import hashlib
+    a = _as_u8(data)
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    out = C.c_void_p()
+    olen, nb = C.c_size_t(), C.c_size_t()
+    rc = lib().orc_encode_mt(_ptr(a), a.size, level, threads, C.byref(out), C.byref(olen), C.byref(nb))
+    if rc != 0:
+        raise ValueError("level out of range")
+    try:
+        if digest:
+            view = (C.c_uint8 * olen.value).from_address(out.value)
+            return hashlib.sha256(view).hexdigest(), olen.value, nb.value
+        return C.string_at(out.value, olen.value)
+    finally:
+        lib().orc_free(out)
 
 
 class BitWriter:

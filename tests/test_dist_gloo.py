@@ -76,3 +76,60 @@ def test_single_process_defaults():
         for k, v in env.items():
             if v is not None:
                 os.environ[k] = v
+
+
+GATE_WORKER = r"""
+import os, sys, json, time
+sys.path.insert(0, %r)
+from banzai_b200 import dist as D
+g = D.Group(backend="gloo")
+gate = D.CpuGate(g)
+# the one-stream measurement of bench.py: rank 0 works, the other ranks wait in the CPU gate
+def sync_all():
+    gate.wait()
+    g.barrier()
+sync_all()
+t0 = time.perf_counter()
+if g.rank == 0:
+    time.sleep(0.4)                 # stands in for rank 0 driving every GPU
+sync_all()
+tmax = g.max_over_ranks(time.perf_counter() - t0)
+print(json.dumps({"rank": g.rank, "tmax": tmax}))
+gate.close()
+g.close()
+""" % ROOT
+
+
+def test_idle_ranks_wait_in_cpu_gate():
+    import json
+    port = _free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", GATE_WORKER], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        so, se = p.communicate(timeout=240)
+        assert p.returncode == 0, se[-2000:]
+        outs.append(json.loads(so.strip().splitlines()[-1]))
+    for o in outs:
+        assert 0.39 < o["tmax"] < 5.0          # the idle rank was held until rank 0 finished
+
+
+def test_reference_arm_runs_without_the_product_library():
+    """bench.py --impl reference: whole workload through the block-parallel oracle driver, and the
+    product package is never imported on that arm"""
+    import json
+    code = ("import sys; sys.argv=['bench.py','--impl','reference','--workload','text-10MB-L9','--steps','1',"
+            "'--warmup','0']; sys.path.insert(0, %r); import bench; bench.main(); "
+            "assert not any(m.startswith('banzai_b200') for m in sys.modules), 'product imported'" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["scaling"] == "strong"
+    assert line["config"]["workload"] == "text-10MB-L9" and line["config"]["bytes"] == 10 * 1000 * 1000
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and line["gpu_launches"] == 0
+    assert line["stream"]["blocks"] >= 11

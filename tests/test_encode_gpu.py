@@ -226,4 +226,4 @@ def test_upload_in_pieces_automatic_mode():
         plain = c.encode_bytes(data, 3)
         assert c.stats()["n_devices"] == 1
     assert got == plain
-    assert bz2.decompress(got) == data.tobytes()
+    assert got == O.encode_mt(data, 3)
