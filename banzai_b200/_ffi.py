@@ -34,6 +34,7 @@ class Stats(C.Structure):
         ("bwt_rounds_total", C.c_uint64), ("bwt_algorithmic_bytes", C.c_uint64),
         ("bwt_cyc_build", C.c_uint64), ("bwt_cyc_radix", C.c_uint64), ("bwt_cyc_rerank", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("bwt_sum_tile", C.c_uint64), ("bwt_cyc_tile", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -42,7 +43,8 @@ class Stats(C.Structure):
 
 class BwtBlockStats(C.Structure):
     _fields_ = [("n", C.c_uint32), ("rounds", C.c_uint32), ("tied", C.c_uint32), ("pad", C.c_uint32),
-                ("sum_active", C.c_uint64), ("sum_active_passes", C.c_uint64), ("cycles", C.c_uint64)]
+                ("sum_active", C.c_uint64), ("sum_active_passes", C.c_uint64), ("cycles", C.c_uint64),
+                ("sum_tile", C.c_uint64)]
 
 
 _vp, _sz = C.c_void_p, C.c_size_t

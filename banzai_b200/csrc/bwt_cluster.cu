@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) bwt_cluster_kernel(BwtA
         cluster.sync();
         const u32 qpos = __ldcg(&ctl->blk);
         if (qpos >= a.n_blocks) break;
-        const u32 blk = a.order ? a.order[qpos] : qpos;
+        const u32 blk = qpos;
 
         const u8 *S = a.rle + a.blk_off[blk];
         u8 *bwt_out = a.bwt + a.blk_off[blk];
@@ -637,6 +637,8 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) bwt_cluster_kernel(BwtA
             st.pad = 0;
             st.sum_active = sum_active;
             st.sum_active_passes = sum_active_passes;
+            st.sum_tile = 0;
+            st.cyc_tile = 0;
             st.cyc_build = (u64)cyc_build;
             st.cyc_radix = (u64)cyc_radix;
             st.cyc_rerank = (u64)cyc_rerank;

@@ -1,5 +1,5 @@
 // bwt_sort.cu — K3/K4: Burrows-Wheeler transform of many independent bzip2 blocks by a
-// cyclic prefix-doubling rotation sort (hand-written LSD radix sort, sm_100a).
+// cyclic prefix-doubling rotation sort with in-shared-memory group refinement (sm_100a).
 //
 // Replaces the SA-IS pass of the reference (lib/bwt.rs:526-756) and reproduces its
 // contract exactly: bwt[k] = byte preceding the k-th smallest rotation; rotations are
@@ -9,132 +9,113 @@
 // Execution model (B200-first): one persistent CTA per bzip2 block slot.  A CTA claims a
 // block from an atomic queue and runs the WHOLE doubling loop for it on its own: no
 // inter-CTA synchronisation, no host round trip for the early exit, and blocks that need
-// 3 rounds do not wait for blocks that need 20.  With >= 2 x 148 blocks in flight the
-// chip is covered; per-CTA state (2 x 8 B records + 4 B rank per byte) streams through HBM.
+// 3 rounds do not wait for blocks that need 20.
 //
-// Per block of n bytes S:
-//   records are 64-bit  [ key:40 | idx:20 ]   (n <= 900 000 < 2^20)
-//   round 0   : key = S[i..i+5) (cyclic)                           -> sort -> rank_5
-//   round h   : key = (rank_h[i] : 20, rank_h[(i+h) mod n] : 20)   -> sort -> rank_2h
-//   only rotations whose rank is still shared ("active") are re-sorted; a rotation whose
-//   key became unique gets its final rank and drops out of later rounds.
+// Per block of n bytes S (n <= 900 000 < 2^20):
+//   round 0 : 64-bit records [ key:40 | idx:20 ], key = S[i..i+5) (cyclic); five LSD radix
+//             passes through HBM (TMA-streamed tiles, see radix_pass); the re-rank step gives
+//             every rotation the position of its group's first record as rank[i] and leaves the
+//             ACTIVE LIST: the records [ rank:20 | idx:20 ] of all rotations whose 5-byte key is
+//             shared, in sorted order, so that every group is a contiguous run of the list.
+//   round h : (h = 5, 10, 20, ...) a group only has to be sorted by rank[idx + h] WITHIN
+//             itself.  The list is walked in tiles of whole groups (<= 4096 records): one
+//             coalesced read of the list, one gather of rank[idx + h], a stable LSD radix sort of
+//             (group number in tile : 12, rank[idx+h] : 20) entirely in shared memory, new ranks
+//             from head-flag bitmaps, one scatter of the changed ranks, and the records that
+//             still share their key go back to the list in place (order-preserving compaction).
+//             A round therefore moves a record through HBM once instead of five times.  Groups
+//             larger than a tile (long repeats, periodic data) take the global path: keys
+//             [ rank : rank[idx+h] : idx ] are written out and sorted by the 20 bits of
+//             rank[idx+h] with the radix passes of round 0 (the passes whose digit is the same in
+//             every record are skipped: three instead of five).
+//   rank[] is updated in place while a round runs.  A group's ranks are all replaced between
+//   two CTA barriers and no group is read (as rank[idx+h]) and written in the same phase, so a
+//   reader sees every group either completely refined or not at all — both are consistent
+//   with the final order, the refined one merely carries more information.
 //   A round that splits no group proves the remaining groups are identical rotations
 //   (period | n); their positions inside the group are arbitrary for the BWT bytes and
 //   origPtr = group base + group size - 1.
 //   Last, one pass in index order writes bwt[rank[i]] = S[i-1] (coalesced reads, a one-byte
 //   scatter that covers the block's output at once and merges in L2).
-//
-// Radix pass (per tile of TILE records, sequential over tiles inside the CTA so that the
-// running bucket cursors live in shared memory): TMA bulk copy of the next tile while this one
-// is processed, per-warp stable ranking (one ballot per digit bit finds the lanes with the
-// same digit, one shared atomic with return value per digit group; counters are 16-bit pairs),
-// cross-warp scan, shared-memory reorder, coalesced bucket-run stores with an L2 evict_first
-// policy.  The per-digit histograms of all passes are taken while the records are generated
-// (in the then idle reorder buffer, parked in global memory during the passes), so each pass
-// costs one read + one write of the records.
-// DESIGN.md §4 has the measurements behind these choices (what bounds the kernel, what was
-// tried and dropped).
+// DESIGN.md §4 has the measurements behind these choices.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace bnz {
 namespace bwt {
 
-// Phase timing of the radix pass for tools/bwt_phase_prof.py (`make prof` builds a second library
-// with -DBWT_PHASE_PROF=<thread id>): cycles of thread BWT_PHASE_PROF of every CTA between the
-// marks, summed over the launch.  Compiled out of the product library.
-#ifdef BWT_PHASE_PROF
-__device__ unsigned long long g_prof[8];
-#define PROF_DECL long long prof_t[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, prof_prev = clock64(), prof_now
-#define PROF_MARK(i) (prof_now = clock64(), prof_t[i] += prof_now - prof_prev, prof_prev = prof_now)
-#define PROF_FLUSH()                                                                               \
-    do {                                                                                           \
-        if (threadIdx.x == BWT_PHASE_PROF)                                                         \
-            for (int i_ = 0; i_ < 8; i_++) atomicAdd(&g_prof[i_], (unsigned long long)prof_t[i_]); \
-    } while (0)
-#else
-#define PROF_DECL
-#define PROF_MARK(i)
-#define PROF_FLUSH()
-#endif
-
-#ifndef BWT_T
-#define BWT_T 512
-#endif
-constexpr int T = BWT_T;             // threads per CTA
+constexpr int T = 512;               // threads per CTA
 constexpr int NW = T / 32;           // warps per CTA
-#ifndef BWT_K
-#define BWT_K 8
-#endif
-#ifndef BWT_MINCTA
-#define BWT_MINCTA (1024 / BWT_T)
-#endif
-constexpr int K = BWT_K;             // records per thread per tile
+constexpr int K = 8;                 // records per thread per tile
 constexpr int TILE = T * K;          // 4096 records = 32 KB
+constexpr int BITS = 8;              // radix digit
+constexpr int BINS = 1 << BITS;
+constexpr int WORDS = BINS / 2;      // packed counter words per warp row (two 16-bit bins per word)
 constexpr int KEY_BITS = 40;
+constexpr int PASSES = KEY_BITS / BITS;
 constexpr int IDX_BITS = 20;
 constexpr u32 IDX_MASK = (1u << IDX_BITS) - 1u;
 constexpr u32 RANK_MASK = (1u << 20) - 1u;
 constexpr u32 DONE = 0x80000000u;
-constexpr int MAX_ROUNDS = 40;
+constexpr int MAX_ROUNDS = 48;
+constexpr int BMW = TILE / 32;       // words of a per-tile bitmap
+static_assert(WORDS <= T && BMW == 128 && NW == 16, "scan layouts below assume 512 threads, 4096-record tiles");
 
-template <int BITS>
-struct Cfg {
-    static constexpr int BINS = 1 << BITS;
-    static constexpr int PASSES = (KEY_BITS + BITS - 1) / BITS;
-    static constexpr int BPT = (BINS + T - 1) / T;      // bins per thread in the bin scans
-};
-
-template <int BITS>
 struct __align__(128) Smem {
-    u64 inbuf[TILE];                                      // TMA landing zone for the next tile
-    u64 stage[TILE];                                      // tile reorder buffer (digit histograms while keys are built)
-    u32 whist[NW][Cfg<BITS>::BINS / 2];                   // per-warp digit counts / offsets, two 16-bit bins per word
-    u32 cursor[Cfg<BITS>::BINS];                          // running bucket cursors (global)
-    u32 gbase[Cfg<BITS>::BINS];                           // cursor - binoff
-    u16 binoff[Cfg<BITS>::BINS];                          // exclusive bin offsets inside the tile
+    u64 buf0[TILE];                  // TMA landing zone of the global passes | ping buffer of the in-tile sort
+    u64 buf1[TILE];                  // reorder buffer of the global passes (digit histograms while keys are built) | pong
+    u32 whist[NW][WORDS];            // per-warp digit counts / offsets, two 16-bit bins per word
+    u32 cursor[BINS];                // running bucket cursors of a global pass
+    u32 gbase[BINS];                 // cursor - binoff
+    u16 binoff[BINS];                // exclusive bin offsets inside the tile
+    u32 r1tab[TILE];                 // tile path: rank (= position of the first record) of each group of the tile
+    u32 bm_k[BMW], bm_g[BMW], bm_a[BMW];      // per position: key head | group head | stays active
+    u32 pre_k[BMW], pre_g[BMW], pre_a[BMW];   // per bitmap word: last head before it (1-based) | active records before it
     u64 scratch64[40];
-    u64 mbar;                                             // mbarrier of the TMA tile pipeline
+    u64 mbar;                        // mbarrier of the TMA tile pipeline
     u32 scratch[40];
-    u32 s_count;                                          // records appended by build_*
-    u32 s_list;                                           // active-list length appended by rerank
-    u32 s_block;                                          // claimed block id
-    u32 s_flags[8];                                       // per pass: every record has the same digit
-    u8 present[256];                                      // has_byte
+    u32 wcnt[NW], wlast[NW];         // tile path: group heads per warp, last head position per warp
+    u32 s_count;                     // records appended by build_*
+    u32 s_block;                     // claimed block id
+    u32 s_tot;                       // tile path: records that stay active in this tile
+    u32 s_la;                        // tile path: the record after the tile starts a new group
+    u32 s_min;                       // group-end search
+    u32 s_flags[8];                  // per pass: every record has the same digit
+    u64 acc[8];                      // per block statistics, kept by thread 0 (see ACC_*)
+    u8 present[256];                 // has_byte
 };
-static_assert(Cfg<10>::PASSES * Cfg<10>::BINS * 4 <= TILE * 8, "histograms must fit the reorder buffer");
+enum { ACC_ACTIVE = 0, ACC_PASSES, ACC_TILE, ACC_CYC_BUILD, ACC_CYC_RADIX, ACC_CYC_RERANK, ACC_CYC_TILE };
 
 // per-pass digit histograms: built in the (then idle) reorder buffer, parked in global memory
-template <int BITS>
-__device__ __forceinline__ u32 *hist_of(Smem<BITS> &sm) { return reinterpret_cast<u32 *>(sm.stage); }
+__device__ __forceinline__ u32 *hist_of(Smem &sm) { return reinterpret_cast<u32 *>(sm.buf1); }
 
-template <int BITS>
-__device__ __forceinline__ u32 digit_of(u64 rec, int pass)
+__device__ __forceinline__ u32 digit_of(u64 rec, int pass) { return (u32)(rec >> (IDX_BITS + pass * BITS)) & (u32)(BINS - 1); }
+
+__device__ __forceinline__ u32 lanemask_le()
 {
-    return (u32)(rec >> (IDX_BITS + pass * BITS)) & (u32)(Cfg<BITS>::BINS - 1);
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
 }
 
-template <int BITS>
-__device__ __forceinline__ void hist_clear(Smem<BITS> &sm)
+__device__ __forceinline__ void hist_clear(Smem &sm)
 {
     u32 *hist = hist_of(sm);
-    for (int i = threadIdx.x; i < Cfg<BITS>::PASSES * Cfg<BITS>::BINS; i += T) hist[i] = 0;
+    for (int i = threadIdx.x; i < PASSES * BINS; i += T) hist[i] = 0;
     if (threadIdx.x == 0) sm.s_count = 0;
     __syncthreads();
 }
 
-template <int BITS>
-__device__ __forceinline__ void hist_add(Smem<BITS> &sm, u64 rec)
+__device__ __forceinline__ void hist_add(Smem &sm, u64 rec)
 {
     u32 *hist = hist_of(sm);
 #pragma unroll
-    for (int p = 0; p < Cfg<BITS>::PASSES; p++) atomicAdd(&hist[p * Cfg<BITS>::BINS + digit_of<BITS>(rec, p)], 1u);
+    for (int p = 0; p < PASSES; p++) atomicAdd(&hist[p * BINS + digit_of(rec, p)], 1u);
 }
 
 // Round 0: key = the five bytes S[i..i+5) (cyclic), big-endian, so h = 5 afterwards.
 // S is 16-byte aligned and padded to 16 bytes, so two aligned 32-bit loads cover any 5-byte window.
-template <int BITS>
-__device__ void build_initial(Smem<BITS> &sm, const u8 *__restrict__ S, u32 n, u64 *dst)
+__device__ void build_initial(Smem &sm, const u8 *__restrict__ S, u32 n, u64 *dst)
 {
     hist_clear(sm);
     for (int i = threadIdx.x; i < 256; i += T) sm.present[i] = 0;
@@ -171,58 +152,10 @@ __device__ void build_initial(Smem<BITS> &sm, const u8 *__restrict__ S, u32 n, u
     __syncthreads();
 }
 
-// Round h: append a record for every still-active rotation, scanning rank[] in index order
-// (coalesced reads of rank[i] and rank[i+h]).
-template <int BITS>
-__device__ void build_round(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h,
-                            u64 *dst)
-{
-    hist_clear(sm);
-    const u32 hm = h % n;
-    for (u32 base = 0; base < n; base += TILE) {
-        // all loads first (rank[i], then the rank[i+h] gathers) so their latencies overlap
-        u32 r[K], r2[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            u32 i = base + k * T + threadIdx.x;
-            r[k] = (i < n) ? ld_keep(rank + i) : DONE;
-        }
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            u32 i = base + k * T + threadIdx.x;
-            r2[k] = 0;
-            if (!(r[k] & DONE)) {
-                u32 j = i + hm;
-                if (j >= n) j -= n;
-                r2[k] = ld_keep(rank + j);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            u32 i = base + k * T + threadIdx.x;
-            bool act = !(r[k] & DONE);
-            u64 rec = ((u64)r[k] << (IDX_BITS + 20)) | ((u64)(r2[k] & RANK_MASK) << IDX_BITS) | i;
-            u32 m = __ballot_sync(0xffffffffu, act);
-            if (m) {
-                u32 wbase = 0;
-                if (lane_id() == 0) wbase = atomicAdd(&sm.s_count, (u32)__popc(m));
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (act) {
-                    st_stream(dst + wbase + __popc(m & lanemask_lt()), rec);
-                    hist_add(sm, rec);
-                }
-            }
-        }
-    }
-    __syncthreads();
-}
-
-// warp-wide "which lanes hold my digit": BITS ballots (cheaper than match.any here)
-template <int BITS>
+// warp-wide "which lanes hold my digit": BITS ballots (match.any costs ~1000 cycles on this part)
 __device__ __forceinline__ u32 match_digit(u32 d)
 {
     // peers = lanes whose digit equals mine: AND over the digit's bits of XNOR(ballot(bit), my bit).
-    // Inline PTX keeps it at and/setp + vote + predicated not + and per bit.
     u32 peers = 0xffffffffu;
 #pragma unroll
     for (int b = 0; b < BITS; b++) {
@@ -241,14 +174,40 @@ __device__ __forceinline__ u32 match_digit(u32 d)
     return peers;
 }
 
-// Round h when few rotations are still active: the previous re-rank left the list of active
-// (new rank, idx) pairs, so only those are touched instead of scanning all n ranks.
-template <int BITS>
-__device__ void build_round_list(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h, const u64 *alist, u32 cnt,
-                                 u64 *dst)
+// Stable rank of this warp's records among the warp's records with the same digit.  The warp owns
+// the tile positions [w*256, w*256+256), row k = positions w*256 + 32k + lane.  One shared atomic
+// with return value per digit group and row; atomics of successive rows to the same counter execute
+// in program order, so rows need no barrier.  (A warp holds at most 256 records of a tile, so the
+// 16-bit halves of a counter word never carry.)  Leaves the per-warp digit counts in whist[w].
+__device__ __forceinline__ void rank_rows(Smem &sm, const u64 (&rec)[K], u32 nrows, int pass, u32 (&rk)[K])
+{
+    const u32 lane = lane_id(), w = warp_id();
+    {   // zero this warp's counter row with 16-byte stores
+        uint4 *row = reinterpret_cast<uint4 *>(sm.whist[w]);
+        for (int b = lane; b < WORDS / 4; b += 32) row[b] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        rk[k] = 0;
+        if ((u32)k < nrows) {                                   // (warp-uniform)
+            const u32 d = digit_of(rec[k], pass);
+            const u32 peers = match_digit(d);
+            const u32 leader = 31 - __clz(peers);
+            const u32 sh = (d & 1u) * 16u;
+            u32 bcount = 0;
+            if (lane == leader) bcount = atomicAdd(&sm.whist[w][d >> 1], (u32)__popc(peers) << sh);
+            bcount = __shfl_sync(0xffffffffu, bcount, leader);
+            rk[k] = ((bcount >> sh) & 0xffffu) + __popc(peers & lanemask_lt());
+        }
+    }
+}
+
+// Key of a group that is too large for a tile: [ rank : rank[idx+h] : idx ] for the records
+// alist[0..cnt) (one group of the active list), with the digit histograms of all passes.
+__device__ void build_group(Smem &sm, const u32 *rank, u32 n, u32 hm, const u64 *alist, u32 cnt, u64 *dst)
 {
     hist_clear(sm);
-    const u32 hm = h % n;
     for (u32 base = 0; base < cnt; base += TILE) {
         u64 e[K];
         u32 r2[K];
@@ -272,7 +231,7 @@ __device__ void build_round_list(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h, 
             u32 j = base + k * T + threadIdx.x;
             if (j < cnt) {
                 const u32 idx = (u32)e[k] & IDX_MASK;
-                const u64 r1 = e[k] >> IDX_BITS;
+                const u64 r1 = (e[k] >> IDX_BITS) & RANK_MASK;
                 const u64 rec = (r1 << (IDX_BITS + 20)) | ((u64)r2[k] << IDX_BITS) | idx;
                 st_stream(dst + j, rec);
                 hist_add(sm, rec);
@@ -284,13 +243,10 @@ __device__ void build_round_list(Smem<BITS> &sm, const u32 *rank, u32 n, u32 h, 
     __syncthreads();
 }
 
-// After the keys of a round are built: park the per-pass histograms in global memory (the
-// reorder buffer they were built in is needed by the passes) and note the passes whose digit is
-// the same for every record.
-template <int BITS>
-__device__ void hist_park(Smem<BITS> &sm, u32 *ghist, u32 count)
+// After the keys are built: park the per-pass histograms in global memory (the reorder buffer they
+// were built in is needed by the passes) and note the passes whose digit is the same for every record.
+__device__ void hist_park(Smem &sm, u32 *ghist, u32 count)
 {
-    constexpr int BINS = Cfg<BITS>::BINS, PASSES = Cfg<BITS>::PASSES;
     const u32 *hist = hist_of(sm);
     if (threadIdx.x < 8) sm.s_flags[threadIdx.x] = 0;
     __syncthreads();
@@ -302,18 +258,12 @@ __device__ void hist_park(Smem<BITS> &sm, u32 *ghist, u32 count)
     __syncthreads();
 }
 
-// One LSD pass over `count` records: src -> dst by digit `pass`.
+// One LSD pass over `count` records through HBM: src -> dst by digit `pass`.
 // Tiles are streamed through shared memory with TMA bulk copies (cp.async.bulk + mbarrier):
 // the copy of tile t+1 is in flight while tile t is ranked, reordered and stored.
-template <int BITS>
-__device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, int pass, const u32 *ghist,
-                           u32 &phase)
+__device__ void radix_pass(Smem &sm, const u64 *src, u64 *dst, u32 count, int pass, const u32 *ghist, u32 &phase)
 {
-    constexpr int BINS = Cfg<BITS>::BINS;
-    constexpr int BPT = Cfg<BITS>::BPT;
-    constexpr int WORDS = BINS / 2;                             // packed counter words per warp row
-    constexpr int NSCAN = WORDS < T ? WORDS : T;                // threads that own counter words in the scan
-    static_assert(WORDS <= T, "one counter word per scan thread");
+    constexpr int BPT = (BINS + T - 1) / T;
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
 
     // records were written with generic-proxy stores; order them before the async-proxy reads
@@ -322,7 +272,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
     if (tid == 0) {
         const u32 bytes = (min((u32)TILE, count) * 8u + 15u) & ~15u;
         mbar_expect_tx(&sm.mbar, bytes);
-        tma_load_1d_stream(sm.inbuf, src, bytes, &sm.mbar);
+        tma_load_1d_stream(sm.buf0, src, bytes, &sm.mbar);
     }
 
     // cursor = exclusive scan of this pass's histogram
@@ -345,61 +295,39 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
     }
     __syncthreads();
 
-    PROF_DECL;
     for (u32 base = 0; base < count; base += TILE) {
         const u32 tile_n = min((u32)TILE, count - base);
         u64 rec[K];
         u32 rk[K];
-        {   // zero this warp's counter row with 16-byte stores
-            uint4 *row = reinterpret_cast<uint4 *>(sm.whist[w]);
-            for (int b = lane; b < WORDS / 4; b += 32) row[b] = make_uint4(0, 0, 0, 0);
-        }
-        PROF_MARK(0);                                           // loop overhead + counter zeroing
         mbar_wait(&sm.mbar, phase);
         phase ^= 1u;
-        PROF_MARK(1);                                           // wait for the tile
         const u32 wl = w * (K * 32) + lane;
         if (tile_n == TILE) {
 #pragma unroll
-            for (int k = 0; k < K; k++) rec[k] = sm.inbuf[wl + k * 32];
+            for (int k = 0; k < K; k++) rec[k] = sm.buf0[wl + k * 32];
         } else {
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 u32 j = wl + k * 32;
-                rec[k] = (j < tile_n) ? sm.inbuf[j] : ~0ull;
+                rec[k] = (j < tile_n) ? sm.buf0[j] : ~0ull;
             }
         }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const u32 d = digit_of<BITS>(rec[k], pass);
-            const u32 peers = match_digit<BITS>(d);
-            const u32 leader = 31 - __clz(peers);
-            const u32 sh = (d & 1u) * 16u;
-            // one shared atomic per digit group; its return value is the group's base.  Atomics of
-            // successive rows to the same counter execute in program order, so rows need no barrier.
-            // (a warp holds at most 256 records of a tile, so the 16-bit halves never carry)
-            u32 bcount = 0;
-            if (lane == leader) bcount = atomicAdd(&sm.whist[w][d >> 1], (u32)__popc(peers) << sh);
-            bcount = __shfl_sync(0xffffffffu, bcount, leader);
-            rk[k] = ((bcount >> sh) & 0xffffu) + __popc(peers & lanemask_lt());
-        }
-        PROF_MARK(2);                                           // ranking
-        __syncthreads();                                        // B1: inbuf consumed, whist complete
-        PROF_MARK(3);                                           // wait at B1
+        rank_rows(sm, rec, K, pass, rk);
+        __syncthreads();                                        // B1: buf0 consumed, whist complete
 
         if (tid == 0 && base + TILE < count) {                  // prefetch the next tile
             const u32 nb = (min((u32)TILE, count - base - TILE) * 8u + 15u) & ~15u;
-            // no proxy fence here: every thread's reads of inbuf have returned (their values feed the
-            // ranking above) and B1 orders them before this copy; a fence.proxy.async in this spot
-            // costs a GPU-scope MEMBAR per tile that stalls the whole CTA behind warp 0
+            // Write-after-read across proxies: every thread's generic reads of buf0 have returned (their
+            // values feed the ranking above) and B1 orders them before this copy is issued.  This is the
+            // consumer-release / producer-acquire handshake of every TMA pipeline (no proxy fence on the
+            // release side); a fence.proxy.async here compiles to a GPU-scope MEMBAR per tile.
             mbar_expect_tx(&sm.mbar, nb);
-            tma_load_1d_stream(sm.inbuf, src + base + TILE, nb, &sm.mbar);
+            tma_load_1d_stream(sm.buf0, src + base + TILE, nb, &sm.mbar);
         }
 
         // cross-warp exclusive scan per bin (two bins per packed word; a tile holds 4096 records, so
         // the halves never carry), then exclusive scan over bins
-        if (tid < NSCAN) {
+        if (tid < WORDS) {
             u32 run = 0;
 #pragma unroll
             for (int ww = 0; ww < NW; ww++) {
@@ -410,7 +338,7 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             const u32 lo = run & 0xffffu, hi = run >> 16, sum = lo + hi;
             const u32 inc = warp_incl_sum(sum);
             if (lane == 31) sm.scratch[w] = inc;
-            asm volatile("bar.sync 1, %0;" ::"n"(NSCAN) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(WORDS) : "memory");
             u32 woff = 0;
             for (u32 q = 0; q < w; q++) woff += sm.scratch[q];
             const u32 ex = woff + inc - sum;
@@ -424,56 +352,48 @@ __device__ void radix_pass(Smem<BITS> &sm, const u64 *src, u64 *dst, u32 count, 
             sm.cursor[b0 + 1] = cur1 + hi;
         }
         __syncthreads();                                        // B2
-        PROF_MARK(4);                                           // scan (B1 -> B2)
 
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            const u32 d = digit_of<BITS>(rec[k], pass);
+            const u32 d = digit_of(rec[k], pass);
             const u32 pos = sm.binoff[d] + ((sm.whist[w][d >> 1] >> ((d & 1u) * 16u)) & 0xffffu) + rk[k];
-            sm.stage[pos] = rec[k];
+            sm.buf1[pos] = rec[k];
         }
         __syncthreads();                                        // B3
-        PROF_MARK(5);                                           // reorder (B2 -> B3)
 
         if (tile_n == TILE) {
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const u32 j = k * T + tid;
-                const u64 r = sm.stage[j];
-                st_stream(dst + sm.gbase[digit_of<BITS>(r, pass)] + j, r);
+                const u64 r = sm.buf1[j];
+                st_stream(dst + sm.gbase[digit_of(r, pass)] + j, r);
             }
         } else {
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const u32 j = k * T + tid;
                 if (j < tile_n) {
-                    const u64 r = sm.stage[j];
-                    st_stream(dst + sm.gbase[digit_of<BITS>(r, pass)] + j, r);
+                    const u64 r = sm.buf1[j];
+                    st_stream(dst + sm.gbase[digit_of(r, pass)] + j, r);
                 }
             }
         }
-        // no barrier here: the next tile's B1 orders these reads before stage/whist are reused
-        PROF_MARK(6);                                           // bucket stores
+        // no barrier here: the next tile's B1 orders these reads before buf1/whist are reused
     }
-    PROF_FLUSH();
     __syncthreads();
 }
 
 struct RerankOut {
-    u32 active;      // records that still share their key after this round
+    u32 active;      // records that still share their key after this step
     u32 splits;      // key heads that are not group heads (new groups created)
 };
 
-// Walk the sorted records, assign new ranks, retire singletons (writing their BWT byte).
-// `initial`: all records belong to one group with base rank 0 (round 0).
-template <int BITS>
-__device__ RerankOut rerank(Smem<BITS> &sm, const u64 *src, u32 count, bool initial,
-                            const u8 *__restrict__ S, u32 n, u32 *rank,
-                            u8 *__restrict__ bwt_out, u32 *ptr_out, u64 *alist)
+// Walk records sorted by their 40-bit key (round 0: all of the block, `initial`; later: one group
+// that went through the global passes), assign new ranks, retire singletons, and append the
+// records that stay active to the active list at list[out_pos ...] IN SORTED ORDER.
+__device__ RerankOut rerank(Smem &sm, const u64 *src, u32 count, bool initial, u32 *rank, u64 *list, u32 out_pos)
 {
     const u32 tid = threadIdx.x;
-    if (tid == 0) sm.s_list = 0;
-    __syncthreads();
     u32 carry_grp = 0, carry_key = 0;       // 1-based positions of the latest heads so far
     u32 n_active = 0, n_split = 0;
     const u64 grp_mask = initial ? 0ull : ((u64)RANK_MASK << 20);   // bits of r1 inside key40
@@ -512,7 +432,8 @@ __device__ RerankOut rerank(Smem<BITS> &sm, const u64 *src, u32 count, bool init
         const u32 tot_k = (u32)tot2, tot_g = (u32)(tot2 >> 32);
 
         u32 nrv[K];
-        u32 flg[K];                          // bit0 valid, bit1 singleton
+        u32 flg[K];                          // bit0 valid, bit1 singleton, bit2 rank unchanged
+        u32 mine = 0;                        // records of this thread that stay active
 #pragma unroll
         for (int k = 0; k < K; k++) {
             u32 j = j0 + k;
@@ -530,24 +451,18 @@ __device__ RerankOut rerank(Smem<BITS> &sm, const u64 *src, u32 count, bool init
                 // a record that stays in the first subgroup of its old group keeps its rank: its
                 // rank[] entry is already correct, skip the (random, 32-byte-sector) store
                 if (!single && !initial && nrv[k] == r1) flg[k] |= 4u;
-                if (!single) n_active++;
+                if (!single) mine++;
                 if (hk && !hg) n_split++;
             }
         }
-        if (alist) {
-            // compact (new rank, idx) of the rotations that stay active (order is irrelevant)
+        // order-preserving compaction: thread t holds K consecutive records
+        u32 tot_a;
+        u32 at = out_pos + n_active + block_excl_sum<T>(mine, sm.scratch, &tot_a);
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                const bool act = (flg[k] & 3u) == 1u;
-                const u32 m = __ballot_sync(0xffffffffu, act);
-                if (m) {
-                    u32 wbase = 0;
-                    if (lane_id() == 0) wbase = atomicAdd(&sm.s_list, (u32)__popc(m));
-                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                    if (act) alist[wbase + __popc(m & lanemask_lt())] = ((u64)nrv[k] << IDX_BITS) | idx[k];
-                }
-            }
+        for (int k = 0; k < K; k++) {
+            if ((flg[k] & 3u) == 1u) st_stream(list + at++, ((u64)nrv[k] << IDX_BITS) | idx[k]);
         }
+        n_active += tot_a;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             if (flg[k] & 1u) {
@@ -563,17 +478,294 @@ __device__ RerankOut rerank(Smem<BITS> &sm, const u64 *src, u32 count, bool init
         carry_grp = max(carry_grp, tot_g);
     }
     RerankOut o;
-    o.active = block_sum<T>(n_active, sm.scratch);
+    o.active = n_active;                     // (block-uniform: sum of the tile totals)
     o.splits = block_sum<T>(n_split, sm.scratch);
     return o;
 }
 
+// One tile of the active list: the whole groups among list[p .. p+TILE), sorted by rank[idx + h]
+// inside shared memory.  Returns the number of list records consumed; 0 = the group that starts at
+// list[p] does not fit a tile (nothing was done).  The records that stay active are written back to
+// list[out_pos ...] (out_pos <= p: the compaction is in place), out_pos advances.
+__device__ u32 refine_tile(Smem &sm, u64 *list, u32 p, u32 count, u32 hm, u32 n, u32 *rank, u32 &out_pos,
+                           u32 &n_active, u32 &n_split)
+{
+    const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    const u32 q0 = w * (K * 32) + lane;
+    const u32 avail = min((u32)TILE, count - p);
+    const bool more = p + TILE < count;                 // records follow this tile
+
+    // ---- records and group heads
+    u64 rec[K];
+    u32 hb[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const u32 q = q0 + k * 32;
+        rec[k] = (q < avail) ? list[p + q] : ~0ull;
+    }
+    u32 left0 = 0xffffffffu;                             // r1 of the record before this warp's first one
+    if (lane == 0 && w > 0 && w * (K * 32) - 1 < avail) left0 = (u32)(list[p + w * (K * 32) - 1] >> IDX_BITS) & RANK_MASK;
+    if (tid == T - 1) {
+        // does the record after the tile start a new group?
+        u32 la = 1;
+        if (more) la = (((u32)(list[p + TILE] >> IDX_BITS) & RANK_MASK) != ((u32)(rec[K - 1] >> IDX_BITS) & RANK_MASK)) ? 1u : 0u;
+        sm.s_la = la;
+    }
+    u32 cnt = 0, last = 0;                               // heads of this warp; last head position + 1 (heads at q >= 1 only)
+    {
+        u32 prev_row_last = left0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 q = q0 + k * 32;
+            const u32 r1 = (u32)(rec[k] >> IDX_BITS) & RANK_MASK;
+            u32 lf = __shfl_up_sync(0xffffffffu, r1, 1);
+            if (lane == 0) lf = prev_row_last;
+            const bool head = q < avail && (q == 0 || r1 != lf);
+            hb[k] = __ballot_sync(0xffffffffu, head);
+            prev_row_last = __shfl_sync(0xffffffffu, r1, 31);
+            cnt += __popc(hb[k]);
+            u32 hq = hb[k];
+            if (w == 0 && k == 0) hq &= ~1u;             // position 0 is a head by construction
+            if (hq) last = w * (K * 32) + k * 32 + (31 - __clz(hq)) + 1;
+        }
+    }
+    if (lane == 0) {
+        sm.wcnt[w] = cnt;
+        sm.wlast[w] = last;
+    }
+    __syncthreads();
+    u32 woff = 0, total = 0, lh = 0;
+#pragma unroll
+    for (int v = 0; v < NW; v++) {
+        const u32 c = sm.wcnt[v];
+        if ((u32)v < w) woff += c;
+        total += c;
+        lh = max(lh, sm.wlast[v]);
+    }
+    u32 tile_n = avail, G = total;
+    if (more && !sm.s_la) {
+        if (lh == 0) return 0;                           // one group fills the tile and goes on (block-uniform)
+        tile_n = lh - 1;                                 // cut at the last head: the groups before it are complete
+        G = total - 1;
+    }
+    const u32 nrows = (tile_n > w * (K * 32)) ? min((u32)K, (tile_n - w * (K * 32) + 31) / 32) : 0u;
+
+    // ---- rank[idx + h], group numbers, sort items [ group:12 | rank[idx+h]:20 | idx:20 ]
+    {
+        u32 r2[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 q = q0 + k * 32;
+            r2[k] = 0;
+            if (q < tile_n) {
+                u32 j = ((u32)rec[k] & IDX_MASK) + hm;
+                if (j >= n) j -= n;
+                r2[k] = ld_keep(rank + j) & RANK_MASK;
+            }
+        }
+        u32 rowbase = woff;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 q = q0 + k * 32;
+            if (q < tile_n) {
+                const u32 g = rowbase + __popc(hb[k] & lanemask_le()) - 1;
+                if ((hb[k] >> lane) & 1u) sm.r1tab[g] = (u32)(rec[k] >> IDX_BITS) & RANK_MASK;
+                rec[k] = ((u64)g << (IDX_BITS + 20)) | ((u64)r2[k] << IDX_BITS) | ((u32)rec[k] & IDX_MASK);
+            } else {
+                rec[k] = ~0ull;
+            }
+            rowbase += __popc(hb[k]);
+        }
+    }
+
+    // ---- stable LSD radix sort of the tile in shared memory (20 + log2(G) key bits)
+    const int npass = (G <= 16) ? 3 : 4;
+    u64 *fin = nullptr;
+    for (int pass = 0; pass < npass; pass++) {
+        u64 *dstb = (pass & 1) ? sm.buf0 : sm.buf1;
+        if (pass > 0) {
+            const u64 *srcb = (pass & 1) ? sm.buf1 : sm.buf0;
+#pragma unroll
+            for (int k = 0; k < K; k++) rec[k] = ((u32)k < nrows) ? srcb[q0 + k * 32] : ~0ull;
+        }
+        u32 rk[K];
+        rank_rows(sm, rec, nrows, pass, rk);
+        __syncthreads();
+        if (tid < WORDS) {
+            u32 run = 0;
+#pragma unroll
+            for (int ww = 0; ww < NW; ww++) {
+                const u32 v = sm.whist[ww][tid];
+                sm.whist[ww][tid] = run;
+                run += v;
+            }
+            const u32 lo = run & 0xffffu, hi = run >> 16, sum = lo + hi;
+            const u32 inc = warp_incl_sum(sum);
+            if (lane == 31) sm.scratch[w] = inc;
+            asm volatile("bar.sync 1, %0;" ::"n"(WORDS) : "memory");
+            u32 wo = 0;
+            for (u32 q = 0; q < w; q++) wo += sm.scratch[q];
+            const u32 ex = wo + inc - sum;
+            sm.binoff[2 * tid] = (u16)ex;
+            sm.binoff[2 * tid + 1] = (u16)(ex + lo);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if ((u32)k < nrows) {
+                const u32 d = digit_of(rec[k], pass);
+                const u32 pos = sm.binoff[d] + ((sm.whist[w][d >> 1] >> ((d & 1u) * 16u)) & 0xffffu) + rk[k];
+                dstb[pos] = rec[k];
+            }
+        }
+        __syncthreads();
+        fin = dstb;
+    }
+
+    // ---- head flags of the sorted tile (kept as bitmaps in shared memory: one word per warp row)
+    u64 *spare = (fin == sm.buf0) ? sm.buf1 : sm.buf0;
+    {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 q = q0 + k * 32;
+            const u32 keyhi = ((u32)k < nrows) ? (u32)(fin[q] >> IDX_BITS) : 0xffffffffu;   // [ group:12 | r2:20 ]
+            u32 lf = __shfl_up_sync(0xffffffffu, keyhi, 1);
+            if (lane == 0) lf = (q > 0 && (u32)k < nrows) ? (u32)(fin[q - 1] >> IDX_BITS) : 0xffffffffu;
+            const bool valid = q < tile_n;
+            const bool ghead = valid && (q == 0 || (keyhi >> 20) != (lf >> 20));
+            const bool khead = valid && (q == 0 || keyhi != lf);
+            const u32 kbw = __ballot_sync(0xffffffffu, khead);
+            const u32 gbw = __ballot_sync(0xffffffffu, ghead);
+            if (lane == 0) {
+                sm.bm_k[w * K + k] = kbw;
+                sm.bm_g[w * K + k] = gbw;
+            }
+        }
+    }
+    __syncthreads();
+    if (w < 2) {
+        // per bitmap word: 1-based position of the last head before the word (exclusive running maximum)
+        const u32 *bm = w ? sm.bm_g : sm.bm_k;
+        u32 *pre = w ? sm.pre_g : sm.pre_k;
+        u32 loc[4], run = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const u32 wd = lane * 4 + j;
+            loc[j] = run;
+            const u32 m = bm[wd];
+            if (m) run = wd * 32 + (31 - __clz(m)) + 1;
+        }
+        const u32 inc = warp_incl_max(run);
+        u32 ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) ex = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) pre[lane * 4 + j] = max(loc[j], ex);
+    }
+    __syncthreads();
+
+    // ---- new ranks, singletons, rank[] scatter; the new list records wait in the spare buffer
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if ((u32)k < nrows) {                                     // (warp-uniform)
+            const u32 q = q0 + k * 32;
+            const u32 wd = w * K + k;
+            const bool valid = q < tile_n;
+            const u32 kbw = sm.bm_k[wd], gbw = sm.bm_g[wd];
+            const u32 mk = kbw & lanemask_le(), mg = gbw & lanemask_le();
+            const u32 pk = mk ? wd * 32 + (31 - __clz(mk)) + 1 : sm.pre_k[wd];
+            const u32 pg = mg ? wd * 32 + (31 - __clz(mg)) + 1 : sm.pre_g[wd];
+            const u64 it = fin[q];
+            const u32 g = (u32)(it >> (IDX_BITS + 20)) & 0xfffu;
+            const u32 id = (u32)it & IDX_MASK;
+            const u32 r1 = valid ? sm.r1tab[g] : 0u;
+            const u32 nr = r1 + (pk - pg);
+            const bool khead = (kbw >> lane) & 1u;
+            u32 nxt;                                              // is position q + 1 a key head (or the end)?
+            if (lane < 31) nxt = (kbw >> (lane + 1)) & 1u;
+            else nxt = (wd + 1 < BMW) ? (sm.bm_k[(wd + 1) & (BMW - 1)] & 1u) : 1u;
+            const bool single = khead && (q + 1 >= tile_n || nxt);
+            const bool active = valid && !single;
+            const u32 abw = __ballot_sync(0xffffffffu, active);
+            if (lane == 0) {
+                sm.bm_a[wd] = abw;
+                n_active += __popc(abw);
+                n_split += __popc(kbw & ~gbw);
+            }
+            if (valid) {
+                if (single) st_keep(rank + id, nr | DONE);
+                else {
+                    if (nr != r1) st_keep(rank + id, nr);        // (the first subgroup keeps its rank)
+                    spare[q] = ((u64)nr << IDX_BITS) | id;
+                }
+            }
+        } else if (lane == 0) {
+            sm.bm_a[w * K + k] = 0;
+        }
+    }
+    __syncthreads();
+    if (w == 0) {
+        u32 loc[4], run = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            loc[j] = run;
+            run += __popc(sm.bm_a[lane * 4 + j]);
+        }
+        const u32 inc = warp_incl_sum(run);
+        const u32 ex = inc - run;
+#pragma unroll
+        for (int j = 0; j < 4; j++) sm.pre_a[lane * 4 + j] = ex + loc[j];
+        if (lane == 31) sm.s_tot = inc;
+    }
+    __syncthreads();
+    // ---- the records that stay active go back to the list, in sorted order
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if ((u32)k < nrows) {
+            const u32 wd = w * K + k;
+            const u32 abw = sm.bm_a[wd];
+            if ((abw >> lane) & 1u) st_stream(list + out_pos + sm.pre_a[wd] + __popc(abw & lanemask_lt()), spare[q0 + k * 32]);
+        }
+    }
+    out_pos += sm.s_tot;
+    __syncthreads();
+    return tile_n;
+}
+
+// first position > p + TILE of the active list whose rank differs from r1p (the list is sorted
+// by rank, the records up to p + TILE are known to carry r1p), or count
+__device__ u32 group_end(Smem &sm, const u64 *list, u32 p, u32 count, u32 r1p)
+{
+    const u32 tid = threadIdx.x;
+    u32 a = p + TILE + 1, b = count;          // answer in [a, b]; every position < a matches, b mismatches (or is the end)
+    if (a > b) a = b;
+    while (a < b) {
+        const u32 span = b - a;
+        const u32 step = (span + T - 1) / T;
+        if (tid == 0) sm.s_min = T;
+        __syncthreads();
+        const u32 pos = a + tid * step;
+        const bool mism = pos >= b || (((u32)(list[pos] >> IDX_BITS) & RANK_MASK) != r1p);
+        if (mism) atomicMin(&sm.s_min, tid);
+        __syncthreads();
+        const u32 f = sm.s_min;
+        __syncthreads();
+        if (f == T) {
+            a = a + (T - 1) * step + 1;
+            if (a > b) a = b;
+        } else {
+            const u32 nb = min(b, a + f * step);
+            if (f > 0) a = a + (f - 1) * step + 1;
+            b = nb;
+            if (a > b) a = b;
+        }
+    }
+    return a;
+}
+
 // Remaining groups are sets of identical rotations: give them distinct positions inside
 // their group (any order yields the same BWT bytes) and derive origPtr by the
-// descending-index rule.
-template <int BITS>
-__device__ void finalize_ties(Smem<BITS> &sm, const u64 *src, u32 count,
-                              const u8 *__restrict__ S, u32 n, const u32 *rank,
+// descending-index rule.  `list` = the active list [ rank:20 | idx:20 ].
+__device__ void finalize_ties(Smem &sm, const u64 *list, u32 count, const u8 *__restrict__ S, u32 n, const u32 *rank,
                               u8 *__restrict__ bwt_out, u32 *ptr_out)
 {
     const u32 tid = threadIdx.x;
@@ -584,13 +776,13 @@ __device__ void finalize_ties(Smem<BITS> &sm, const u64 *src, u32 count,
     for (u32 base = 0; base < count; base += TILE) {
         const u32 j0 = base + tid * K;
         u32 r1[K + 1], idx[K];
-        r1[0] = (j0 > 0 && j0 - 1 < count) ? (u32)(src[j0 - 1] >> (IDX_BITS + 20)) : 0xffffffffu;
+        r1[0] = (j0 > 0 && j0 - 1 < count) ? (u32)(list[j0 - 1] >> IDX_BITS) & RANK_MASK : 0xffffffffu;
         u32 pg[K], mg = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
             u32 j = j0 + k;
-            u64 r = (j < count) ? src[j] : ~0ull;
-            r1[k + 1] = (u32)(r >> (IDX_BITS + 20));
+            u64 r = (j < count) ? list[j] : ~0ull;
+            r1[k + 1] = (u32)(r >> IDX_BITS) & RANK_MASK;
             idx[k] = (u32)r & IDX_MASK;
             if (j < count && (j == 0 || r1[k + 1] != r1[k])) mg = j + 1;
             pg[k] = mg;
@@ -616,12 +808,10 @@ __device__ void finalize_ties(Smem<BITS> &sm, const u64 *src, u32 count,
     if (tid == 0 && zero_tied) *ptr_out = base0 + s0 - 1;
 }
 
-template <int BITS>
-__global__ void __launch_bounds__(T, BWT_MINCTA) bwt_sort_kernel(BwtArgs a)
+__global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem<BITS> &sm = *reinterpret_cast<Smem<BITS> *>(smem_raw);
-    constexpr int PASSES = Cfg<BITS>::PASSES;
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const u32 tid = threadIdx.x;
 
     if (tid == 0) {
@@ -631,84 +821,108 @@ __global__ void __launch_bounds__(T, BWT_MINCTA) bwt_sort_kernel(BwtArgs a)
     __syncthreads();
     u32 phase = 0;                       // parity of the next TMA completion
 
-    u64 *bufA = a.ws_rec + (size_t)blockIdx.x * 2 * a.ws_stride;
-    u64 *bufB = bufA + a.ws_stride;
+    u64 *list = a.ws_rec + (size_t)blockIdx.x * 3 * a.ws_stride;     // the active list
+    u64 *bufC = list + a.ws_stride;                                   // key records of the global passes
+    u64 *bufD = bufC + a.ws_stride;
     u32 *rank = a.ws_rank + (size_t)blockIdx.x * a.ws_stride;
+    u32 *ghist = a.ws_hist + (size_t)blockIdx.x * BWT_HIST_WORDS;
 
     for (;;) {
         if (tid == 0) sm.s_block = atomicAdd(a.next_block, 1u);
         __syncthreads();
-        const u32 qpos = sm.s_block;
+        const u32 blk = sm.s_block;
         __syncthreads();
-        if (qpos >= a.n_blocks) break;
-        const u32 blk = a.order ? a.order[qpos] : qpos;
+        if (blk >= a.n_blocks) break;
 
         const u8 *S = a.rle + a.blk_off[blk];
         u8 *bwt_out = a.bwt + a.blk_off[blk];
         const u32 n = a.blk_len[blk];
         u32 *ptr_out = a.ptr + blk;
 
-        u32 rounds = 0;
-        u64 sum_active = 0, sum_active_passes = 0;
-        long long cyc_build = 0, cyc_radix = 0, cyc_rerank = 0, t0, t1;
-        u32 h = 5;
-        u32 count = n;
-        bool initial = true;
+        u32 rounds = 1;
         bool tied = false;
-        const u64 *alist = nullptr;           // active list left by the previous re-rank (or null)
-        u32 alist_cnt = 0;
+        if (tid == 0) {
+            for (int i = 0; i < 8; i++) sm.acc[i] = 0;
+            sm.acc[ACC_ACTIVE] = n;
+        }
+        auto acc = [&](int which, u64 v) { if (tid == 0) sm.acc[which] += v; };
 
-        while (count > 0 && rounds < MAX_ROUNDS) {
-            t0 = clock64();
-            if (initial) build_initial<BITS>(sm, S, n, bufA);
-            else if (alist) build_round_list<BITS>(sm, rank, n, h, alist, alist_cnt, bufA);
-            else build_round<BITS>(sm, rank, n, h, bufA);
-            count = sm.s_count;
-            t1 = clock64();
-            cyc_build += t1 - t0;
-
-            u32 *ghist = a.ws_hist + (size_t)blockIdx.x * (PASSES * Cfg<BITS>::BINS);
-            hist_park<BITS>(sm, ghist, count);
-            u64 *src = bufA, *dst = bufB;
+        // global passes over `cnt` key records in bufC; returns the buffer that holds the sorted records
+        auto sort_keys = [&](u32 cnt) -> const u64 * {
+            const long long c0 = clock64();
+            hist_park(sm, ghist, cnt);
+            u64 *src = bufC, *dst = bufD;
             u32 passes_run = 0;
             for (int p = 0; p < PASSES; p++) {
                 if (sm.s_flags[p]) continue;               // every record has the same digit: nothing moves
-                radix_pass<BITS>(sm, src, dst, count, p, ghist, phase);
+                radix_pass(sm, src, dst, cnt, p, ghist, phase);
                 u64 *t = src; src = dst; dst = t;
                 passes_run++;
             }
-            sum_active += count;
-            sum_active_passes += (u64)count * passes_run;
-            rounds++;
+            acc(ACC_PASSES, (u64)cnt * passes_run);
+            acc(ACC_CYC_RADIX, (u64)(clock64() - c0));
+            return src;
+        };
 
-            t0 = clock64();
-            cyc_radix += t0 - t1;
-            // few active rotations: let the re-rank leave their list in the tail of the free buffer
-            // (the next key build writes < n/8 records at the front of bufA, the list sits at the end)
-            u64 *next_list = (!initial && (u64)count * 8 < n) ? dst + (a.ws_stride - count) : nullptr;
-            RerankOut ro = rerank<BITS>(sm, src, count, initial, S, n, rank, bwt_out, ptr_out, next_list);
+        // ---- round 0: all rotations by their first five bytes
+        u32 count;
+        {
+            long long c0 = clock64();
+            build_initial(sm, S, n, bufC);
+            acc(ACC_CYC_BUILD, (u64)(clock64() - c0));
+            const u64 *sorted = sort_keys(n);
+            c0 = clock64();
+            RerankOut ro = rerank(sm, sorted, n, true, rank, list, 0);
+            count = ro.active;
             __syncthreads();
-            alist = next_list;
-            alist_cnt = sm.s_list;
-            cyc_rerank += clock64() - t0;
-            if (ro.active > 0 && ro.splits == 0 && !initial) {
-                finalize_ties<BITS>(sm, src, count, S, n, rank, bwt_out, ptr_out);
+            acc(ACC_CYC_RERANK, (u64)(clock64() - c0));
+        }
+
+        // ---- rounds h = 5, 10, 20, ...: refine the groups of the active list
+        u32 h = 5;
+        while (count > 0 && rounds < MAX_ROUNDS) {
+            const u32 hm = h % n;
+            u32 p = 0, out_pos = 0, n_act = 0, n_spl = 0, big_spl = 0;
+            acc(ACC_ACTIVE, count);
+            rounds++;
+            while (p < count) {
+                long long c0 = clock64();
+                const u32 used = refine_tile(sm, list, p, count, hm, n, rank, out_pos, n_act, n_spl);
+                if (used) {
+                    acc(ACC_TILE, used);
+                    acc(ACC_CYC_TILE, (u64)(clock64() - c0));
+                    p += used;
+                    continue;
+                }
+                // a group larger than a tile: sort it by rank[idx + h] through HBM
+                const u32 ge = group_end(sm, list, p, count, (u32)(list[p] >> IDX_BITS) & RANK_MASK);
+                const u32 m = ge - p;
+                build_group(sm, rank, n, hm, list + p, m, bufC);
+                acc(ACC_CYC_BUILD, (u64)(clock64() - c0));
+                const u64 *srt = sort_keys(m);
+                c0 = clock64();
+                RerankOut rg = rerank(sm, srt, m, false, rank, list, out_pos);
+                out_pos += rg.active;
+                big_spl += rg.splits;
+                __syncthreads();
+                acc(ACC_CYC_RERANK, (u64)(clock64() - c0));
+                p = ge;
+            }
+            const u32 splits = block_sum<T>(n_spl, sm.scratch) + big_spl;
+            count = out_pos;
+            if (count > 0 && splits == 0) {
+                finalize_ties(sm, list, count, S, n, rank, bwt_out, ptr_out);
                 tied = true;
                 break;
             }
-            if (!initial) h *= 2;
-            initial = false;
-            count = ro.active;
-            // make this round's rank[] stores visible to every thread of the CTA
-            __threadfence_block();
-            __syncthreads();
+            if (h < (1u << 30)) h *= 2;
+            (void)n_act;
         }
 
         // BWT bytes of every rotation that was ranked uniquely: bwt[rank[i]] = S[i-1].  rank[] and S
         // are read in index order (coalesced); the one-byte scatter covers the block's whole output
         // within this one short pass, so the sectors fill up in L2 instead of costing a 32-byte
-        // DRAM gather per rotation inside the re-rank steps (measured: -5..7 % sort time).
-        __threadfence_block();
+        // DRAM gather per rotation inside the re-rank steps.
         __syncthreads();
         for (u32 base = 0; base < n; base += 4 * T) {
             u32 r[4], c[4];
@@ -734,11 +948,13 @@ __global__ void __launch_bounds__(T, BWT_MINCTA) bwt_sort_kernel(BwtArgs a)
             st.rounds = rounds;
             st.tied = tied ? 1u : 0u;
             st.pad = 0;
-            st.sum_active = sum_active;
-            st.sum_active_passes = sum_active_passes;
-            st.cyc_build = (u64)cyc_build;
-            st.cyc_radix = (u64)cyc_radix;
-            st.cyc_rerank = (u64)cyc_rerank;
+            st.sum_active = sm.acc[ACC_ACTIVE];
+            st.sum_active_passes = sm.acc[ACC_PASSES];
+            st.sum_tile = sm.acc[ACC_TILE];
+            st.cyc_build = sm.acc[ACC_CYC_BUILD];
+            st.cyc_radix = sm.acc[ACC_CYC_RADIX];
+            st.cyc_rerank = sm.acc[ACC_CYC_RERANK];
+            st.cyc_tile = sm.acc[ACC_CYC_TILE];
             a.stats[blk] = st;
         }
         __syncthreads();
@@ -751,107 +967,21 @@ __global__ void __launch_bounds__(T, BWT_MINCTA) bwt_sort_kernel(BwtArgs a)
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// cost predictor: blocks with many long repeats need many doubling rounds.  Windows are sampled
-// by CONTENT (a 4-byte hash decides), so both copies of a repeat are sampled, and a Bloom filter
-// in shared memory tells whether the 24-byte window was seen before.
-// ---------------------------------------------------------------------------------------
-constexpr int PT = 512;
-constexpr u32 BLOOM_BITS = 1u << 19;                 // 64 KB
-__global__ void __launch_bounds__(PT) bwt_predict_kernel(const u8 *__restrict__ rle, const u64 *__restrict__ blk_off,
-                                                        const u32 *__restrict__ blk_len, u32 *__restrict__ score)
-{
-    extern __shared__ u32 bloom[];
-    __shared__ u32 scratch[40];
-    const u32 b = blockIdx.x, tid = threadIdx.x;
-    const u8 *S = rle + blk_off[b];
-    const u32 n = blk_len[b];
-    for (u32 i = tid; i < BLOOM_BITS / 32; i += PT) bloom[i] = 0;
-    __syncthreads();
-    u32 hits = 0;
-    // lanes take consecutive positions (coalesced); 4 positions per thread and iteration
-    for (u32 base = 0; base + 24 <= n; base += PT * 4) {
-        const u32 i0 = base + tid * 4;
-        if (i0 + 28 > n) continue;
-        // 8 bytes starting at i0 cover the four 4-byte windows i0..i0+3
-        u32 lo = 0, hi = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            lo |= (u32)S[i0 + j] << (8 * j);
-            hi |= (u32)S[i0 + 4 + j] << (8 * j);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const u32 w0 = q ? __funnelshift_r(lo, hi, 8 * q) : lo;
-            if (((w0 * 2654435761u) >> 28) != 0) continue;      // content-defined 1/16 sampling
-            const u32 i = i0 + q;
-            u32 h1 = 2166136261u, h2 = 0x9747b28cu;
-#pragma unroll
-            for (int j = 0; j < 24; j++) {
-                u32 c = S[i + j];
-                h1 = (h1 ^ c) * 16777619u;
-                h2 = (h2 + c) * 0xcc9e2d51u;
-                h2 = (h2 << 13) | (h2 >> 19);
-            }
-            h1 &= BLOOM_BITS - 1;
-            h2 &= BLOOM_BITS - 1;
-            u32 o1 = atomicOr(&bloom[h1 >> 5], 1u << (h1 & 31));
-            u32 o2 = atomicOr(&bloom[h2 >> 5], 1u << (h2 & 31));
-            if (((o1 >> (h1 & 31)) & 1u) && ((o2 >> (h2 & 31)) & 1u)) hits++;
-        }
-    }
-    u32 tot = block_sum<PT>(hits, scratch);
-    if (tid == 0) score[b] = tot;
-}
-
 }  // namespace bwt
 
-#ifdef BWT_PHASE_PROF
-extern "C" __attribute__((visibility("default"))) void bnz_prof_read(unsigned long long *out)
-{
-    unsigned long long z[8] = { 0 };
-    cudaMemcpyFromSymbol(out, bwt::g_prof, sizeof z);
-    cudaMemcpyToSymbol(bwt::g_prof, z, sizeof z);
-}
-#endif
+size_t bwt_smem_bytes() { return sizeof(bwt::Smem); }
 
-cudaError_t bwt_predict_launch(const uint8_t *d_rle, const uint64_t *d_blk_off, const uint32_t *d_blk_len,
-                               uint32_t n_blocks, uint32_t *d_score, cudaStream_t stream)
+cudaError_t bwt_max_ctas(int *ctas_per_sm)
 {
-    if (n_blocks == 0) return cudaSuccess;
-    size_t smem = bwt::BLOOM_BITS / 8;
-    cudaError_t e = cudaFuncSetAttribute(bwt::bwt_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem = bwt_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(bwt::bwt_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bwt::bwt_predict_kernel<<<n_blocks, bwt::PT, smem, stream>>>(d_rle, d_blk_off, d_blk_len, d_score);
-    return cudaGetLastError();
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bwt::bwt_sort_kernel, bwt::T, smem);
 }
 
-size_t bwt_smem_bytes(int bits)
+cudaError_t bwt_launch(const BwtArgs &a, int grid, cudaStream_t stream)
 {
-    return bits == 8 ? sizeof(bwt::Smem<8>) : sizeof(bwt::Smem<10>);
-}
-
-int bwt_passes(int bits) { return bits == 8 ? bwt::Cfg<8>::PASSES : bwt::Cfg<10>::PASSES; }
-
-cudaError_t bwt_max_ctas(int bits, int *ctas_per_sm)
-{
-    cudaError_t e;
-    size_t smem = bwt_smem_bytes(bits);
-    if (bits == 8) {
-        e = cudaFuncSetAttribute(bwt::bwt_sort_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bwt::bwt_sort_kernel<8>, bwt::T, smem);
-    }
-    e = cudaFuncSetAttribute(bwt::bwt_sort_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bwt::bwt_sort_kernel<10>, bwt::T, smem);
-}
-
-cudaError_t bwt_launch(const BwtArgs &a, int bits, int grid, cudaStream_t stream)
-{
-    size_t smem = bwt_smem_bytes(bits);
-    if (bits == 8) bwt::bwt_sort_kernel<8><<<grid, bwt::T, smem, stream>>>(a);
-    else bwt::bwt_sort_kernel<10><<<grid, bwt::T, smem, stream>>>(a);
+    bwt::bwt_sort_kernel<<<grid, bwt::T, bwt_smem_bytes(), stream>>>(a);
     return cudaGetLastError();
 }
 

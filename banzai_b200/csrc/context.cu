@@ -37,7 +37,7 @@ bool device_init(Device &d, int id)
     cudaDeviceProp prop;
     int prio_lo = 0, prio_hi = 0;
     bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaGetDeviceProperties(&prop, d.id) == cudaSuccess &&
-              prop.major >= 10 &&        // kernels are built for sm_100a only; fail loudly
+              prop.major == 10 && prop.minor == 0 &&   // the library holds sm_100a SASS only (no PTX): fail loudly elsewhere
               cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess &&
               // the sort's persistent CTAs must win every SM slot over the work that fills its tail
               cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
@@ -56,7 +56,7 @@ void device_release(Device &d)
     cudaSetDevice(d.id);
     if (d.stream) cudaStreamSynchronize(d.stream);
     for (DevBuf *b : { &d.in, &d.rle, &d.bwt, &d.blk_off, &d.blk_len, &d.ptr, &d.has_byte,
-                       &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.ws_hist, &d.bwt_score, &d.bwt_order, &d.ch_lasthead, &d.ch_meta,
+                       &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.ws_hist, &d.ch_lasthead, &d.ch_meta,
                        &d.ch_restsum, &d.ch_oin, &d.ch_P, &d.ch_tiles, &d.rle_blocks, &d.crc_acc, &d.seg_base,
                        &d.seg_list, &d.seg_cnt, &d.seg_state, &d.num_names, &d.syms, &d.sym_off,
                        &d.sym_len, &d.freqs, &d.mtf_ids, &d.mtf_cseg, &d.lens, &d.codes, &d.tf, &d.num_tables, &d.num_sel,
@@ -129,11 +129,6 @@ extern "C" void bnz_ctx_destroy(bnz_ctx *ctx)
 extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
 {
     if (!ctx || !key) return BNZ_EINVAL;
-    if (!strcmp(key, "bwt_radix_bits")) {
-        if (value != 8 && value != 10) return BNZ_EINVAL;
-        ctx->radix_bits = (int)value;
-        return BNZ_OK;
-    }
     if (!strcmp(key, "bwt_cluster")) {
         if (value < -1 || value > BWT_CLUSTER_MAX) return BNZ_EINVAL;
         ctx->bwt_cluster = (int)value;
@@ -181,11 +176,6 @@ extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
     if (!strcmp(key, "stream_window_bytes")) {
         if (value < (1 << 16)) return BNZ_EINVAL;
         ctx->stream_window_bytes = (size_t)value;
-        return BNZ_OK;
-    }
-    if (!strcmp(key, "bwt_lpt")) {
-        if (value < 0 || value > 2) return BNZ_EINVAL;
-        ctx->bwt_lpt = (int)value;       // 0 off, 1 longest first, 2 light blocks last
         return BNZ_OK;
     }
     if (!strcmp(key, "bwt_cluster_below")) {

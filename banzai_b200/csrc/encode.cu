@@ -142,6 +142,8 @@ static void add_stats(bnz_stats &st, const Shard &sh)
         st.bwt_n += b.n;
         st.bwt_sum_active += b.sum_active;
         st.bwt_sum_active_passes += b.sum_active_passes;
+        st.bwt_sum_tile += b.sum_tile;
+        st.bwt_cyc_tile += b.cyc_tile;
         st.bwt_rounds_total += b.rounds;
         st.bwt_max_rounds = std::max(st.bwt_max_rounds, b.rounds);
         st.bwt_tied_blocks += b.tied;
@@ -149,7 +151,7 @@ static void add_stats(bnz_stats &st, const Shard &sh)
         st.bwt_cyc_radix += b.cyc_radix;
         st.bwt_cyc_rerank += b.cyc_rerank;
     }
-    st.bwt_algorithmic_bytes = 9 * st.bwt_n + 16 * st.bwt_sum_active_passes + 36 * st.bwt_sum_active;
+    st.bwt_algorithmic_bytes = bwt_algorithmic_bytes(st);
     st.kernel_launches += sh.d->launches;
 }
 
@@ -183,7 +185,7 @@ void finish_stats(bnz_ctx *ctx, std::vector<Shard> &shards, bool have_d2h)
     uint32_t busy = 0;
     for (const Shard &sh : shards) busy += sh.blocks.empty() ? 0u : 1u;
     st.n_devices = std::max<uint32_t>(st.n_devices, busy);
-    st.bwt_radix_bits = (uint32_t)ctx->radix_bits;
+    st.bwt_radix_bits = 8;
 }
 
 uint32_t fold_stream_crc(const std::vector<uint32_t> &crcs)       // lib.rs:108
@@ -784,8 +786,9 @@ extern "C" int bnz_encode_device(bnz_ctx *ctx, const void *d_in, const uint8_t *
     *out_len = 0;
     if (level < 1 || level > 9) return fail(ctx, BNZ_EINVAL, "level must be in 1..=9 (lib/lib.rs:89)");
     if (in_len == 0 || !d_in || !h_in) return BNZ_EINVAL;
-    for (Device &dv : ctx->devs)
-        if (dv.id != ctx->devs[0].id) return fail(ctx, BNZ_EINVAL, "bnz_encode_device needs a single-GPU context");
+    if (ctx->devs.size() != 1) return fail(ctx, BNZ_EINVAL, "bnz_encode_device needs a single-GPU context");
+    // the RLE1 and CRC kernels read the input with 16-byte vector loads
+    if (((uintptr_t)d_in & 15) != 0) return fail(ctx, BNZ_EINVAL, "d_in must be 16-byte aligned");
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.in_bytes = in_len;
     Device &d = ctx->devs[0];

@@ -79,7 +79,7 @@ struct Device {
     cudaStream_t stream2 = nullptr;     // side stream: block CRCs run beside the sort
     cudaStream_t stream3[3] = {};       // low-priority streams: MTF of finished blocks fills the sort's tail
     // arenas (grown on demand, kept across calls)
-    DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, ws_hist, bwt_score, bwt_order;
+    DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, ws_hist;
     DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, ch_tiles, rle_blocks, crc_acc;
     DevBuf seg_base, seg_list, seg_cnt, seg_state, num_names, syms, sym_off, sym_len, freqs, mtf_ids, mtf_cseg;
     DevBuf lens, codes, tf, num_tables, num_sel, span_base, hdr, hdr_bits, crc, blk_bits, blk_bitoff,
@@ -100,12 +100,9 @@ struct bnz_ctx {
     std::vector<Device> devs;
     std::string err;
     bnz_stats stats;
-    int radix_bits = 8;
     int ctas_per_sm = 0;
     int bwt_cluster = -1;         // CTAs per bzip2 block (-1: auto, 0/1: single-CTA kernel)
     int bwt_threads = 512;
-    int bwt_lpt = 0;                   // longest-predicted-first work queue (measured: no robust gain, off)
-    std::vector<uint32_t> last_scores; // predictor output of the last sort (debug / tests)
     int bwt_cluster_below = 400;       // auto mode: cluster kernel when a device gets fewer blocks than this
     // cached pinned output buffer handed to the caller by bnz_encode / returned by bnz_free
     uint8_t *out_cache = nullptr;
@@ -220,6 +217,16 @@ struct Shard {
 };
 
 // K1 emit .. K7 + headers for one shard; ends with a host sync that yields block_bits.
+
+// SURVEY §8(d) algorithmic bytes of the BWT sort, per record and round:
+//   sorted through HBM : 16 per radix pass executed (read + write of the 8-byte record) + 36
+//                        (8 histogram/key write, 8 + 4 re-rank read + rank write, 4 + 4 rank gathers, 8 list record)
+//   sorted in shared memory: 24 (8 list read, 4 rank gather, 4 rank write, 8 list write)
+// plus 9 per byte of the block (text read, initial 8-byte key).
+inline uint64_t bwt_algorithmic_bytes(const bnz_stats &s)
+{
+    return 9 * s.bwt_n + 16 * s.bwt_sum_active_passes + 36 * (s.bwt_sum_active - s.bwt_sum_tile) + 24 * s.bwt_sum_tile;
+}
 
 void put_bits_host(uint8_t *buf, uint64_t bitpos, uint64_t value, int nbits);      // MSB first
 uint32_t fold_stream_crc(const std::vector<uint32_t> &crcs);                       // lib.rs:108

@@ -64,8 +64,9 @@ struct BwtStats {                 // per bzip2 block, written by the sort kernel
     uint32_t tied;                // 1 if the block had identical rotations (period | n)
     uint32_t pad;
     uint64_t sum_active;          // sum over rounds of records sorted (a_r)
-    uint64_t sum_active_passes;   // sum over rounds of a_r * radix passes executed (P_r)
-    uint64_t cyc_build, cyc_radix, cyc_rerank;   // SM cycles spent per phase (thread 0's clock64)
+    uint64_t sum_active_passes;   // sum over rounds of (records sorted through HBM) * radix passes executed (P_r)
+    uint64_t sum_tile;            // records (summed over rounds) that were sorted inside shared memory (no HBM pass)
+    uint64_t cyc_build, cyc_radix, cyc_rerank, cyc_tile;   // SM cycles spent per phase (thread 0's clock64)
 };
 
 constexpr int BWT_HIST_WORDS = 5 * 1024;
@@ -79,24 +80,17 @@ struct BwtArgs {
     BwtStats *stats;              // [n_blocks] or nullptr
     uint32_t *next_block;         // work-queue counter (zeroed by the host)
     uint32_t n_blocks;
-    uint64_t *ws_rec;             // per CTA: 2 * ws_stride records
+    uint64_t *ws_rec;             // per CTA: 3 (one-CTA kernel) | 2 (cluster kernel) * ws_stride records
     uint32_t *ws_rank;            // per CTA: ws_stride ranks
     size_t ws_stride;             // >= max block length (+ cluster slack), multiple of 16
     uint32_t *ws_hist;            // one-CTA kernel: per CTA BWT_HIST_WORDS words (per-pass digit histograms)
     void *ws_ctl;                 // cluster kernel only: per cluster BWT_CTL_BYTES of control state
-    const uint32_t *order;        // optional: queue position -> block id (longest-first schedule)
     uint32_t *done;               // optional [n_blocks], host-mapped: set to 1 (release.sys) when a block's outputs are complete
 };
 
-// cheap per-block cost predictor for the work queue: counts content-sampled 24-byte windows that
-// were seen before inside the block (Bloom filter in shared memory)
-cudaError_t bwt_predict_launch(const uint8_t *d_rle, const uint64_t *d_blk_off, const uint32_t *d_blk_len,
-                               uint32_t n_blocks, uint32_t *d_score, cudaStream_t stream);
-
-size_t bwt_smem_bytes(int bits);
-int bwt_passes(int bits);
-cudaError_t bwt_max_ctas(int bits, int *ctas_per_sm);
-cudaError_t bwt_launch(const BwtArgs &a, int bits, int grid, cudaStream_t stream);
+size_t bwt_smem_bytes();
+cudaError_t bwt_max_ctas(int *ctas_per_sm);
+cudaError_t bwt_launch(const BwtArgs &a, int grid, cudaStream_t stream);
 // cluster-cooperative variant (bwt_cluster.cu)
 size_t bwtc_smem_bytes(int threads);
 cudaError_t bwtc_max_clusters(int threads, int C, int *n_clusters);

@@ -28,7 +28,6 @@ int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt
     a.n_blocks = n_blocks;
     a.ws_ctl = nullptr;
     a.ws_hist = nullptr;
-    a.order = nullptr;
     a.done = nullptr;
 
     // auto: many blocks -> one persistent CTA per block (best aggregate throughput);
@@ -57,43 +56,12 @@ int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt
     }
 
     int per_sm = 0;
-    CK(ctx, bwt_max_ctas(ctx->radix_bits, &per_sm));
+    CK(ctx, bwt_max_ctas(&per_sm));
     if (per_sm <= 0) return fail(ctx, BNZ_ECUDA, "bwt kernel does not fit on an SM");
     if (ctx->ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->ctas_per_sm);
     int grid = (int)std::min<uint64_t>((uint64_t)n_blocks, (uint64_t)d.sm_count * per_sm);
-    if (ctx->bwt_lpt && n_blocks > (uint32_t)grid) {
-        // blocks differ several-fold in sort cost (doubling rounds); with a plain index-order queue
-        // the last wave's long blocks leave most SMs idle.  Predict, then schedule longest first.
-        CK(ctx, d.bwt_score.ensure((size_t)n_blocks * 4));
-        CK(ctx, d.bwt_order.ensure((size_t)n_blocks * 4));
-        CK(ctx, bwt_predict_launch(d_rle, d_blk_off, d_blk_len, n_blocks, d.bwt_score.as<uint32_t>(), d.stream));
-        d.launches++;
-        std::vector<uint32_t> score(n_blocks), order(n_blocks);
-        CK(ctx, cudaMemcpyAsync(score.data(), d.bwt_score.p, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, d.stream));
-        CK(ctx, cudaStreamSynchronize(d.stream));
-        ctx->last_scores = score;
-        if (ctx->bwt_lpt == 1) {
-            // full longest-first order
-            for (uint32_t i = 0; i < n_blocks; i++) order[i] = i;
-            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return score[x] > score[y]; });
-        } else {
-            // "light tail": keep the natural (type-interleaved) order, but move the `grid` cheapest
-            // blocks to the end of the queue so that the last wave consists of short blocks
-            std::vector<uint32_t> by(n_blocks);
-            for (uint32_t i = 0; i < n_blocks; i++) by[i] = i;
-            std::stable_sort(by.begin(), by.end(), [&](uint32_t x, uint32_t y) { return score[x] < score[y]; });
-            std::vector<uint8_t> tail(n_blocks, 0);
-            for (int i = 0; i < grid; i++) tail[by[i]] = 1;
-            uint32_t k = 0;
-            for (uint32_t i = 0; i < n_blocks; i++) if (!tail[i]) order[k++] = i;
-            for (uint32_t i = 0; i < n_blocks; i++) if (tail[i]) order[k++] = i;
-        }
-        CK(ctx, cudaMemcpyAsync(d.bwt_order.p, order.data(), (size_t)n_blocks * 4, cudaMemcpyHostToDevice, d.stream));
-        CK(ctx, cudaStreamSynchronize(d.stream));      // `order` is a stack vector
-        a.order = d.bwt_order.as<uint32_t>();
-    }
     size_t stride = ((size_t)max_len + 15) & ~(size_t)15;
-    CK(ctx, d.ws_rec.ensure((size_t)grid * 2 * stride * sizeof(uint64_t)));
+    CK(ctx, d.ws_rec.ensure((size_t)grid * 3 * stride * sizeof(uint64_t)));
     CK(ctx, d.ws_rank.ensure((size_t)grid * stride * sizeof(uint32_t)));
     CK(ctx, d.ws_hist.ensure((size_t)grid * BWT_HIST_WORDS * 4));
     a.ws_hist = d.ws_hist.as<uint32_t>();
@@ -104,7 +72,7 @@ int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt
         a.done = d_done;
         if (done_armed) *done_armed = true;
     }
-    CK(ctx, bwt_launch(a, ctx->radix_bits, grid, d.stream));
+    CK(ctx, bwt_launch(a, grid, d.stream));
     d.launches++;
     return BNZ_OK;
 }
@@ -163,12 +131,14 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
     s.n_blocks = (uint32_t)n_blocks;
     s.n_devices = 1;
     s.kernel_launches = 1;
-    s.bwt_radix_bits = (uint32_t)ctx->radix_bits;
+    s.bwt_radix_bits = 8;
     s.bwt_ms = ms;
     for (size_t b = 0; b < n_blocks; b++) {
         s.bwt_n += st[b].n;
         s.bwt_sum_active += st[b].sum_active;
         s.bwt_sum_active_passes += st[b].sum_active_passes;
+        s.bwt_sum_tile += st[b].sum_tile;
+        s.bwt_cyc_tile += st[b].cyc_tile;
         s.bwt_rounds_total += st[b].rounds;
         s.bwt_max_rounds = std::max(s.bwt_max_rounds, st[b].rounds);
         s.bwt_tied_blocks += st[b].tied;
@@ -179,13 +149,14 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
             stats_out[b].n = st[b].n;
             stats_out[b].rounds = st[b].rounds;
             stats_out[b].tied = st[b].tied;
-            stats_out[b].pad = b < ctx->last_scores.size() ? ctx->last_scores[b] : 0;
+            stats_out[b].pad = 0;
+            stats_out[b].sum_tile = st[b].sum_tile;
             stats_out[b].sum_active = st[b].sum_active;
             stats_out[b].sum_active_passes = st[b].sum_active_passes;
-            stats_out[b].cycles = st[b].cyc_build + st[b].cyc_radix + st[b].cyc_rerank;
+            stats_out[b].cycles = st[b].cyc_build + st[b].cyc_radix + st[b].cyc_rerank + st[b].cyc_tile;
         }
     }
-    s.bwt_algorithmic_bytes = 9 * s.bwt_n + 16 * s.bwt_sum_active_passes + 36 * s.bwt_sum_active;
+    s.bwt_algorithmic_bytes = bwt_algorithmic_bytes(s);
     return BNZ_OK;
 }
 

@@ -51,11 +51,12 @@ BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
 
 /* tunables (call before encoding). keys:
  *   "bwt_cluster"        -1 auto | 0 one CTA per block | 2..16 CTAs (one cluster) per block
- *   "bwt_cluster_below"  auto mode: cluster kernel when a device gets fewer blocks than this (400)
+ *   "bwt_cluster_below"  auto mode: cluster kernel when a device gets fewer blocks than this
  *   "bwt_threads"        512 | 1024, cluster kernel
- *   "bwt_radix_bits"     8 | 10, one-CTA kernel (10 measured slower)
  *   "bwt_ctas_per_sm"    0 = auto
- *   "bwt_lpt"            0 index-order work queue | 1 longest-predicted first | 2 light blocks last
+ *   "reuse_input"        1: the caller encodes the SAME host buffer again and again (benchmarks);
+ *                        every device keeps its copy of the input resident, the next call of the
+ *                        identical (pointer, length) skips the upload
  *   "mtf_overlap"        percent of a device's blocks whose MTF may run beside the sort, in the SM
  *                        slots its tail leaves empty (70; 0 = strictly after the sort)
  *   "mtf_groups"         number of block lists the overlapped MTF is issued in (2)
@@ -88,7 +89,10 @@ BNZ_API void bnz_free(bnz_ctx *ctx, uint8_t *p);
  * first device and the stream left on the device (used to time the kernels without
  * PCIe).  h_in is the host mirror of the same bytes: the sequential block-cut walk
  * (lib/rle.rs capacity rule) reads <= 2 KiB of it per block; nothing is uploaded.
- * d_out must hold bnz_max_compressed_size(in_len) bytes (or the exact size if known). */
+ * Needs a context with exactly one device.  d_in must be 16-byte aligned (the kernels read it
+ * with vector loads; memory from bnz_device_alloc is) — BNZ_EINVAL otherwise.  d_out_cap must be
+ * at least the stream size + 8 bytes (the stream is written in whole words):
+ * bnz_max_compressed_size(in_len) always suffices. */
 BNZ_API int bnz_encode_device(bnz_ctx *ctx, const void *d_in, const uint8_t *h_in, size_t in_len,
                               int level, void *d_out, size_t d_out_cap, size_t *out_len);
 BNZ_API size_t bnz_max_compressed_size(size_t in_len);
@@ -152,9 +156,12 @@ typedef struct bnz_stats {
     uint32_t bwt_max_rounds;
     uint32_t bwt_tied_blocks;
     uint64_t bwt_rounds_total;
-    uint64_t bwt_algorithmic_bytes;  /* n + 8n + sum a_r * (16 P_r + 36)   */
+    uint64_t bwt_algorithmic_bytes;  /* 9n + sum over rounds: records sorted through HBM * (16 P_r + 36)
+                                        + records sorted inside shared memory * 24   */
     uint64_t bwt_cyc_build, bwt_cyc_radix, bwt_cyc_rerank;   /* SM cycles per phase, summed over blocks */
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t bwt_sum_tile;           /* of bwt_sum_active: records sorted inside shared memory (no HBM pass) */
+    uint64_t bwt_cyc_tile;           /* SM cycles of that path */
 } bnz_stats;
 BNZ_API int bnz_get_stats(const bnz_ctx *ctx, bnz_stats *out);
 
@@ -193,6 +200,7 @@ typedef struct bnz_bwt_block_stats {
     uint32_t n, rounds, tied, pad;
     uint64_t sum_active, sum_active_passes;
     uint64_t cycles;              /* SM cycles the block occupied its CTA / cluster */
+    uint64_t sum_tile;            /* of sum_active: records sorted inside shared memory */
 } bnz_bwt_block_stats;
 BNZ_API int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t *blk_off,
                           const uint32_t *blk_len, size_t n_blocks, int level, uint8_t *bwt_out,

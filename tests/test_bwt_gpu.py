@@ -22,17 +22,12 @@ def ctx():
     c.close()
 
 
-MODES = {8: [("cluster", 8), ("cluster", 16), ("cluster", 2), ("single", 8)], 10: [("single", 10)]}
+MODES = [("cluster", 8), ("cluster", 16), ("cluster", 2), ("single", 0)]
 
 
-def _check(ctx, blocks, level=9, bits=(8, 10)):
-    modes = [m for b in bits for m in MODES[b]]
-    for kind, val in modes:
-        if kind == "cluster":
-            ctx.set("bwt_cluster", val)
-        else:
-            ctx.set("bwt_cluster", 0)
-            ctx.set("bwt_radix_bits", val)
+def _check(ctx, blocks, level=9):
+    for kind, val in MODES:
+        ctx.set("bwt_cluster", val)
         got = ctx.stage_bwt(blocks, level, with_stats=True)
         for blk, (bw, ptr, has, st) in zip(blocks, got):
             ebw, eptr, ehas = O.bwt(blk)
@@ -86,10 +81,10 @@ def test_periodic_equal_rotations_and_deep_doubling(ctx):
 def test_full_blocks_level9(ctx, kind):
     data = corpus.by_name(kind, 2 * 899999 + 12345)
     blocks = [data[:899999].tobytes(), data[899999:2 * 899999].tobytes(), data[2 * 899999:].tobytes()]
-    _check(ctx, blocks, level=9, bits=(8,) if kind != "text" else (8, 10))
+    _check(ctx, blocks, level=9)
 
 
 def test_many_blocks_more_than_ctas(ctx):
     data = corpus.mixed(700 * 20000)
     blocks = [data[i * 20000:(i + 1) * 20000].tobytes() for i in range(700)]
-    _check(ctx, blocks, level=1, bits=(8,))
+    _check(ctx, blocks, level=1)

@@ -118,30 +118,42 @@ def test_size_independent_properties_at_scale(ctx):
     assert out1 == out2
 
 
-def test_lanes_on_one_gpu_and_device_resident_entry():
-    """several concurrent block batches ("lanes") on the same GPU, and bnz_encode_device, give the
-    same bytes as the plain call"""
+def test_device_resident_entry():
+    """bnz_encode_device (input and stream stay in device memory) gives the bytes of the plain call;
+    it needs a one-device context and a 16-byte aligned input, and says so"""
     import ctypes as C
 
     import banzai_b200
     from banzai_b200 import _ffi
+    from banzai_b200.api import BanzaiError
     data = corpus.mixed(9 * 1000 * 1000)
     want = O.encode(data, 9)
-    for lanes in (1, 2, 3):
-        with banzai_b200.Context(devices=[0] * lanes) as c:
-            assert c.encode_bytes(data, 9) == want
-            lib = _ffi.lib
-            n = data.size
-            d_in = lib.bnz_device_alloc(c._h, n + 64)
-            cap = n + (1 << 20)
-            d_out = lib.bnz_device_alloc(c._h, cap)
-            c._check(lib.bnz_memcpy_h2d(c._h, d_in, data.ctypes.data_as(C.c_void_p), n))
-            olen = c.encode_device(d_in, data.ctypes.data_as(C.c_void_p), n, 9, d_out, cap)
-            back = np.zeros(olen, np.uint8)
-            c._check(lib.bnz_memcpy_d2h(c._h, back.ctypes.data_as(C.c_void_p), d_out, olen))
-            assert back.tobytes() == want
-            lib.bnz_device_free(c._h, d_in)
-            lib.bnz_device_free(c._h, d_out)
+    lib = _ffi.lib
+    n = data.size
+    with banzai_b200.Context(devices=[0]) as c:
+        assert c.encode_bytes(data, 9) == want
+        d_in = lib.bnz_device_alloc(c._h, n + 64)
+        cap = len(want) + 8                       # the documented minimum: stream size + 8
+        d_out = lib.bnz_device_alloc(c._h, cap)
+        c._check(lib.bnz_memcpy_h2d(c._h, d_in, data.ctypes.data_as(C.c_void_p), n))
+        olen = c.encode_device(d_in, data.ctypes.data_as(C.c_void_p), n, 9, d_out, cap)
+        back = np.zeros(olen, np.uint8)
+        c._check(lib.bnz_memcpy_d2h(c._h, back.ctypes.data_as(C.c_void_p), d_out, olen))
+        assert back.tobytes() == want
+        with pytest.raises(BanzaiError):          # misaligned device input
+            c.encode_device(C.c_void_p(d_in + 1), data.ctypes.data_as(C.c_void_p), n - 1, 9, d_out, cap)
+        with pytest.raises(BanzaiError):          # output buffer too small
+            c.encode_device(d_in, data.ctypes.data_as(C.c_void_p), n, 9, d_out, len(want))
+        assert c.encode_bytes(data, 9) == want    # the context is still usable
+        lib.bnz_device_free(c._h, d_in)
+        lib.bnz_device_free(c._h, d_out)
+    with banzai_b200.Context(devices=[0, 0]) as c2:
+        d_in = lib.bnz_device_alloc(c2._h, n + 64)
+        d_out = lib.bnz_device_alloc(c2._h, n)
+        with pytest.raises(BanzaiError):
+            c2.encode_device(d_in, data.ctypes.data_as(C.c_void_p), n, 9, d_out, n)
+        lib.bnz_device_free(c2._h, d_in)
+        lib.bnz_device_free(c2._h, d_out)
 
 
 def test_streaming_batches_do_not_change_the_stream():
