@@ -8,6 +8,7 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "mixed"
 nb = int(sys.argv[2]) if len(sys.argv) > 2 else 296
 level = int(sys.argv[3]) if len(sys.argv) > 3 else 9
 modes = [int(x) for x in (sys.argv[4] if len(sys.argv) > 4 else "0,8").split(",")]
+sets = [kv.split("=") for kv in sys.argv[5:]]
 blk = 100000 * level - 1
 if kind == "ab":
     data = corpus.periodic(nb * blk, b"ab")
@@ -17,6 +18,8 @@ else:
     data = corpus.by_name(kind, nb * blk)
 blocks = [data[i * blk:(i + 1) * blk] for i in range(nb)]
 ctx = banzai_b200.Context(n_gpus=1)
+for k, v in sets:
+    ctx.set(k, int(v))
 for clu in modes:
     ctx.set("bwt_cluster", clu)
     best = None
@@ -31,5 +34,5 @@ for clu in modes:
           f"({gbs / 6550 * 100:.1f}% of 6550), rounds avg {best['bwt_rounds_total'] / nb:.1f} max {best['bwt_max_rounds']}, "
           f"sum_active/n {best['bwt_sum_active'] / best['bwt_n']:.2f} (in smem {best['bwt_sum_tile'] / best['bwt_n']:.2f}), "
           f"HBM passes/n {best['bwt_sum_active_passes'] / best['bwt_n']:.2f}, "
-          f"Gcyc build/radix/rerank/tile {best['bwt_cyc_build'] / 1e9:.2f}/{best['bwt_cyc_radix'] / 1e9:.2f}/"
-          f"{best['bwt_cyc_rerank'] / 1e9:.2f}/{best['bwt_cyc_tile'] / 1e9:.2f}", flush=True)
+          f"Mcyc/block build/radix/rerank/tile {best['bwt_cyc_build'] / 1e6 / nb:.1f}/{best['bwt_cyc_radix'] / 1e6 / nb:.1f}/"
+          f"{best['bwt_cyc_rerank'] / 1e6 / nb:.1f}/{best['bwt_cyc_tile'] / 1e6 / nb:.1f}", flush=True)
