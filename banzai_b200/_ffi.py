@@ -17,7 +17,7 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH)
 
-OK, EINVAL, ECUDA, ENOMEM, EINTERNAL, EIO = 0, 1, 2, 3, 4, 5
+OK, EINVAL, ECUDA, ENOMEM, EINTERNAL, EIO, EVERIFY = 0, 1, 2, 3, 4, 5, 6
 
 
 class Stats(C.Structure):

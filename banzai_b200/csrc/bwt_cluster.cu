@@ -627,6 +627,14 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) bwt_cluster_kernel(BwtA
             if (tot_active == 0) break;
         }
 
+        if (a.marks) {
+            // rows of the rotations 0, 4096, ... for the self-verification (every CTA's rank stores are
+            // visible after the cluster barrier that ended the last round)
+            cluster.sync();
+            if (c == 0)
+                for (u32 i = tid * VERIFY_SPACING; i < n; i += T * VERIFY_SPACING)
+                    a.marks[(size_t)blk * VERIFY_MARKS + i / VERIFY_SPACING] = ld_keep_cg(rank + i) & RANK_MASK;
+        }
         for (int i = tid; i < 256; i += T)
             if (sm.present[i]) a.has_byte[(size_t)blk * 256 + i] = 1;
         if (c == 0 && tid == 0 && a.stats) {

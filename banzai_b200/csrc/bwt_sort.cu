@@ -937,8 +937,11 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
                 c[k] = (i < n) ? S[i == 0 ? n - 1 : i - 1] : 0u;
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++)
+            for (int k = 0; k < 4; k++) {
                 if (r[k] & DONE) bwt_out[r[k] & RANK_MASK] = (u8)c[k];
+                const u32 i = base + k * T + tid;
+                if (a.marks && i < n && (i % VERIFY_SPACING) == 0) a.marks[(size_t)blk * VERIFY_MARKS + i / VERIFY_SPACING] = r[k] & RANK_MASK;
+            }
         }
         if (tid == 0 && (rank[0] & DONE)) *ptr_out = rank[0] & RANK_MASK;
         if (tid < 256) a.has_byte[(size_t)blk * 256 + tid] = sm.present[tid];

@@ -51,11 +51,41 @@ static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t
     CK(ctx, cudaHostGetDevicePointer((void **)&d_done, d.h_done.p, 0));
     CK(ctx, cudaEventRecord(d.ev[12], d.stream));
     bool armed = false;
+    const bool verify = ctx->verify != 0;
+    if (verify) {
+        CK(ctx, d.v_marks.ensure((size_t)nb * VERIFY_MARKS * 4));
+        CK(ctx, d.v_lfl.ensure((size_t)rle_total * 4 + 64));
+        CK(ctx, d.v_flags.ensure((size_t)nb * 4));
+        CK(ctx, cudaMemsetAsync(d.v_flags.p, 0, (size_t)nb * 4, d.stream));
+        CK(ctx, cudaMemsetAsync(d.v_marks.p, 0xff, (size_t)nb * VERIFY_MARKS * 4, d.stream));
+    }
+    // (verify: the MTF must not overwrite the RLE1 images while they are being checked, so nothing
+    // runs beside the sort)
     rc = run_bwt_device(ctx, d, d.rle.as<uint8_t>(), d.bwt.as<uint8_t>(), d.blk_off.as<uint64_t>(),
                         d.blk_len.as<uint32_t>(), nb, bt.max_len, d.ptr.as<uint32_t>(), d.has_byte.as<uint8_t>(),
-                        d.bwt_stats.as<BwtStats>(), ctx->mtf_overlap > 0 ? d_done : nullptr, &armed);
+                        d.bwt_stats.as<BwtStats>(), (ctx->mtf_overlap > 0 && !verify) ? d_done : nullptr, &armed,
+                        verify ? d.v_marks.as<uint32_t>() : nullptr);
     if (rc != BNZ_OK) return rc;
     CK(ctx, cudaEventRecord(d.ev[3], d.stream));
+    if (verify) {
+        VerifyArgs va;
+        va.in_base = in_base;
+        va.rle = d.rle.as<uint8_t>();
+        va.bwt = d.bwt.as<uint8_t>();
+        va.ptr = d.ptr.as<uint32_t>();
+        va.blk_off = d.blk_off.as<uint64_t>();
+        va.blk_len = d.blk_len.as<uint32_t>();
+        va.blocks = d.rle_blocks.as<RleBlock>();
+        va.n_blocks = nb;
+        va.lfl = d.v_lfl.as<uint32_t>();
+        va.marks = d.v_marks.as<uint32_t>();
+        va.stats = d.bwt_stats.as<BwtStats>();
+        va.flags = d.v_flags.as<uint32_t>();
+        va.corrupt = ctx->verify_corrupt >= 1 && ctx->verify_corrupt <= 3 ? ctx->verify_corrupt : 0;
+        CK(ctx, verify_launch(va, d.stream, &d.launches));
+        sh.vflags.assign(nb, 0);
+        CK(ctx, cudaMemcpyAsync(sh.vflags.data(), d.v_flags.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, d.stream));
+    }
 
     // K5 (the RLE1 images are dead once their block is sorted: their buffer holds the MTF index
     // bytes).  The one-CTA-per-block sort ends in a long tail (blocks differ 5x in cost and only
@@ -114,6 +144,11 @@ static int shard_model(bnz_ctx *ctx, Shard &sh, const uint8_t *in_base, uint64_t
     CK(ctx, cudaMemcpyAsync(sh.bst.data(), d.bwt_stats.p, (size_t)nb * sizeof(BwtStats), cudaMemcpyDeviceToHost, d.stream));
     CK(ctx, cudaEventRecord(d.ev[5], d.stream));
     CK(ctx, cudaStreamSynchronize(d.stream));
+    for (uint32_t b = 0; b < (uint32_t)sh.vflags.size(); b++)
+        if (sh.vflags[b])
+            return fail(ctx, BNZ_EVERIFY, std::string("block at input offset ") + std::to_string(sh.blocks[b].s) +
+                                              ((sh.vflags[b] & VERIFY_BAD_RLE) ? ": the RLE1 image does not decode to the input" : "") +
+                                              ((sh.vflags[b] & VERIFY_BAD_BWT) ? ": the inverse BWT is not the RLE1 image" : ""));
     return BNZ_OK;
 }
 
@@ -195,16 +230,69 @@ uint32_t fold_stream_crc(const std::vector<uint32_t> &crcs)       // lib.rs:108
     return s;
 }
 
-static int ensure_out_cache(bnz_ctx *ctx, size_t nbytes)
+static int ensure_out_cache(bnz_ctx *ctx, size_t nbytes, bool exact = false)
 {
     if (ctx->out_cache_cap < nbytes + 16) {
         if (ctx->out_cache) cudaFreeHost(ctx->out_cache);
         ctx->out_cache = nullptr;
         ctx->out_cache_cap = 0;
-        size_t want = nbytes + nbytes / 4 + 4096;
+        size_t want = exact ? nbytes + 4096 : nbytes + nbytes / 4 + 4096;
         CK(ctx, cudaHostAlloc((void **)&ctx->out_cache, want, cudaHostAllocPortable));
         ctx->out_cache_cap = want;
     }
+    return BNZ_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// "verify", host part: the cut chain must cover in[0, covered) without gap or overlap, and the
+// block CRCs the device computed must equal an independent recomputation on the host cores
+// (plain table-driven CRC-32/BZIP2, MSB first, lib/crc32.rs:31-48).
+// ---------------------------------------------------------------------------------------
+static uint32_t host_crc32_bzip2(const uint8_t *p, size_t n)
+{
+    static uint32_t tab[256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (uint32_t b = 0; b < 256; b++) {
+            uint32_t c = b << 24;
+            for (int k = 0; k < 8; k++) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : (c << 1);
+            tab[b] = c;
+        }
+    });
+    uint32_t crc = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; i++) crc = (crc << 8) ^ tab[(crc >> 24) ^ p[i]];
+    return ~crc;
+}
+
+int verify_host(bnz_ctx *ctx, const uint8_t *h_in, uint64_t covered, const std::vector<Shard> &shards)
+{
+    struct Item { uint64_t s, c; uint32_t crc; };
+    std::vector<Item> items;
+    for (const Shard &sh : shards)
+        for (size_t b = 0; b < sh.blocks.size(); b++) items.push_back({ sh.blocks[b].s, sh.blocks[b].c, sh.crcs[b] });
+    uint64_t at = 0;
+    for (const Item &it : items) {
+        if (it.s != at || it.c <= it.s) return fail(ctx, BNZ_EVERIFY, "the block cuts do not tile the input");
+        at = it.c;
+    }
+    if (at != covered) return fail(ctx, BNZ_EVERIFY, "the block cuts do not cover the input");
+    std::atomic<size_t> next{0};
+    std::atomic<long long> bad{-1};
+    const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)items.size()));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([&] {
+            for (size_t k; (k = next.fetch_add(1)) < items.size();) {
+                uint32_t c = host_crc32_bzip2(h_in + items[k].s, (size_t)(items[k].c - items[k].s));
+                if (ctx->verify_corrupt == 4 && k == 0) c ^= 1u;           // test hook
+                if (c != items[k].crc) bad.store((long long)k);
+            }
+        });
+    for (std::thread &t : th) t.join();
+    if (bad.load() >= 0)
+        return fail(ctx, BNZ_EVERIFY, "block CRC differs from the host recomputation at input offset " +
+                                          std::to_string(items[(size_t)bad.load()].s));
     return BNZ_OK;
 }
 
@@ -268,6 +356,9 @@ static int encode_sharded(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level
     int walk_rc = 0;
     uint64_t used = 0;
     HostBarrier bar((int)G);
+    std::mutex bits_mu;
+    std::condition_variable bits_cv;
+    std::vector<char> bits_known(G, 0);
 
     auto work = [&](size_t g) -> int {
         Shard &sh = shards[g];
@@ -385,6 +476,47 @@ static int encode_sharded(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level
             }
             return shard_model(ctx, sh, in_base, N, oin, P, level);
         });
+        // ---- the shard's bit phase is known as soon as the shards before it have been modelled: pack
+        // and download it right away, under the sort of the devices that are still busy
+        {
+            std::unique_lock<std::mutex> lk(bits_mu);
+            bits_known[g] = 1;
+            bits_cv.notify_all();
+            bits_cv.wait(lk, [&] {
+                if (abort_all.load()) return true;
+                for (size_t q = 0; q < g; q++)
+                    if (!bits_known[q]) return false;
+                return true;
+            });
+        }
+        step([&]() -> int {
+            if (!ctx->early_out.o || sh.blocks.empty()) return BNZ_OK;
+            uint64_t bits = bit_base;
+            bool first = true;                                   // no shard before this one holds blocks
+            for (size_t q = 0; q < g; q++) {
+                bits += shards[q].block_bits;
+                if (!shards[q].blocks.empty()) first = false;
+            }
+            sh.bit_base = bits;
+            size_t bytes = 0;
+            int prc = shard_pack(ctx, sh, &bytes);
+            if (prc != BNZ_OK) return prc;
+            const size_t w0 = (size_t)(sh.bit_base >> 5) * 4;
+            if (w0 + bytes + 64 > ctx->early_out.cap) return BNZ_OK;     // does not fit: packed after the join
+            uint8_t *o = ctx->early_out.o;
+            if (first && bit_base == 32) {
+                CK(ctx, cudaMemcpyAsync(o + w0, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
+            } else {
+                CK(ctx, cudaMemcpyAsync(&sh.first_word, d.out.p, 4, cudaMemcpyDeviceToHost, d.stream));
+                if (bytes > 4)
+                    CK(ctx, cudaMemcpyAsync(o + w0 + 4, d.out.as<uint8_t>() + 4, bytes - 4, cudaMemcpyDeviceToHost, d.stream));
+            }
+            CK(ctx, cudaEventRecord(d.ev[7], d.stream));
+            CK(ctx, cudaStreamSynchronize(d.stream));
+            sh.d2h_bytes = bytes;
+            sh.packed = true;
+            return BNZ_OK;
+        });
         if (!resident) uploaded += std::min<uint64_t>(N, cb * RLE_CHUNK + slop) - a;
         sh.h2d_bytes = uploaded;
         if (ctx->reuse_input && rc == BNZ_OK) d.tag(h_in, N, a, b);
@@ -397,6 +529,11 @@ static int encode_sharded(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level
         th.emplace_back([&, g]() {
             t_err_sink = &shards[g].err;
             shards[g].rc = work(g);
+            if (shards[g].rc != BNZ_OK) {
+                std::lock_guard<std::mutex> lk(bits_mu);
+                abort_all.store(true);
+                bits_cv.notify_all();
+            }
             t_err_sink = nullptr;
         });
     for (std::thread &t : th) t.join();
@@ -577,9 +714,24 @@ static int encode_pieces(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level,
 // block is left for the next batch; *consumed tells where it starts).  `bit_base`: bit offset of
 // the batch's first block in the stream.  Leaves every shard's bits in its device's d.out and
 // returns the layout; the callers move the bytes.
+static int encode_all_impl(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, size_t N, int level,
+                           std::vector<Shard> &shards, std::vector<uint32_t> &crcs, uint64_t *total_bits, bool final,
+                           uint64_t bit_base, uint64_t *consumed);
+
 int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, size_t N, int level,
                std::vector<Shard> &shards, std::vector<uint32_t> &crcs, uint64_t *total_bits, bool final,
                uint64_t bit_base, uint64_t *consumed)
+{
+    uint64_t used = 0;
+    int rc = encode_all_impl(ctx, h_in, d_in0, N, level, shards, crcs, total_bits, final, bit_base, &used);
+    if (consumed) *consumed = used;
+    if (rc == BNZ_OK && ctx->verify && !shards.empty()) rc = verify_host(ctx, h_in, final ? (uint64_t)N : used, shards);
+    return rc;
+}
+
+static int encode_all_impl(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, size_t N, int level,
+                           std::vector<Shard> &shards, std::vector<uint32_t> &crcs, uint64_t *total_bits, bool final,
+                           uint64_t bit_base, uint64_t *consumed)
 {
     Device &d0 = ctx->devs[0];
     bnz_stats &st = ctx->stats;
@@ -640,12 +792,15 @@ int encode_all(bnz_ctx *ctx, const uint8_t *h_in, const uint8_t *d_in0, size_t N
 int pack_and_download(bnz_ctx *ctx, std::vector<Shard> &shards, uint8_t *o, bool stream_start,
                       size_t o_first_byte)
 {
-    std::vector<uint32_t> first_word(shards.size(), 0);
     size_t first = 0;                                        // the first shard that holds blocks
     while (first < shards.size() && shards[first].blocks.empty()) first++;
     for (size_t g = 0; g < shards.size(); g++) {
         Shard &sh = shards[g];
         if (sh.blocks.empty()) continue;
+        if (sh.packed) {                                     // (done by the shard's own thread, encode_sharded)
+            ctx->stats.d2h_bytes += sh.d2h_bytes;
+            continue;
+        }
         Device &d = *sh.d;
         CK(ctx, cudaSetDevice(d.id));
         size_t bytes = 0;
@@ -655,7 +810,7 @@ int pack_and_download(bnz_ctx *ctx, std::vector<Shard> &shards, uint8_t *o, bool
         if (g == first && stream_start) {
             CK(ctx, cudaMemcpyAsync(o + w0, d.out.p, bytes, cudaMemcpyDeviceToHost, d.stream));
         } else {
-            CK(ctx, cudaMemcpyAsync(&first_word[g], d.out.p, 4, cudaMemcpyDeviceToHost, d.stream));
+            CK(ctx, cudaMemcpyAsync(&sh.first_word, d.out.p, 4, cudaMemcpyDeviceToHost, d.stream));
             if (bytes > 4)
                 CK(ctx, cudaMemcpyAsync(o + w0 + 4, d.out.as<uint8_t>() + 4, bytes - 4, cudaMemcpyDeviceToHost, d.stream));
         }
@@ -663,7 +818,7 @@ int pack_and_download(bnz_ctx *ctx, std::vector<Shard> &shards, uint8_t *o, bool
         ctx->stats.d2h_bytes += bytes;
     }
     for (Shard &sh : shards) {
-        if (sh.blocks.empty()) continue;
+        if (sh.blocks.empty() || sh.packed) continue;
         CK(ctx, cudaSetDevice(sh.d->id));
         CK(ctx, cudaStreamSynchronize(sh.d->stream));
     }
@@ -671,7 +826,7 @@ int pack_and_download(bnz_ctx *ctx, std::vector<Shard> &shards, uint8_t *o, bool
     for (size_t g = 0; g < shards.size(); g++) {
         if (shards[g].blocks.empty() || (g == first && stream_start)) continue;
         uint8_t *w = o + ((size_t)(shards[g].bit_base >> 5) * 4 - o_first_byte);
-        const uint8_t *f = reinterpret_cast<const uint8_t *>(&first_word[g]);
+        const uint8_t *f = reinterpret_cast<const uint8_t *>(&shards[g].first_word);
         if ((shards[g].bit_base & 31) == 0) memcpy(w, f, 4);
         else for (int k = 0; k < 4; k++) w[k] |= f[k];
     }
@@ -696,14 +851,26 @@ extern "C" int bnz_encode(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int le
     uint8_t *o = nullptr;
     size_t nbytes = 0;
 
-    if (in_len <= ctx->max_batch_bytes) {
+    if (in_len <= ctx->max_batch_bytes * ctx->devs.size()) {      // (the limit is per device)
         // ---- one batch: the stream is assembled in the context's pinned buffer
         std::vector<Shard> shards;
         if (in_len > 0) {
+            if (ctx->devs.size() > 1) {
+                // several devices: a shard is downloaded by its own thread as soon as its bit phase is known,
+                // so the stream buffer must exist up front (sized for incompressible input; a shard that
+                // does not fit is packed after the exact size is known; the buffer is kept across calls)
+                int rc0 = ensure_out_cache(ctx, in_len + in_len / 8 + ((size_t)64 << 20), true);
+                if (rc0 != BNZ_OK) return rc0;
+                ctx->early_out.o = ctx->out_cache;
+                ctx->early_out.cap = ctx->out_cache_cap;
+            }
             int rc = encode_all(ctx, in, nullptr, in_len, level, shards, crcs, &total_bits);
+            ctx->early_out.o = nullptr;
             if (rc != BNZ_OK) return rc;
         }
         nbytes = (size_t)((total_bits + 80 + 7) / 8);
+        if (ctx->out_cache_cap < nbytes + 8 + 16)               // the buffer is about to be replaced: nothing in it counts
+            for (Shard &sh : shards) sh.packed = false;
         int rc = ensure_out_cache(ctx, nbytes + 8);
         if (rc != BNZ_OK) return rc;
         o = ctx->out_cache;
@@ -723,7 +890,7 @@ extern "C" int bnz_encode(bnz_ctx *ctx, const uint8_t *in, size_t in_len, int le
         // partial block is re-read by the next batch.  The stream grows in an ordinary host buffer
         // sized for the worst case up front: untouched pages cost nothing, and nothing is ever
         // copied or cleared in bulk.
-        size_t pos = 0, win = ctx->max_batch_bytes;
+        size_t pos = 0, win = ctx->max_batch_bytes * ctx->devs.size();
         const size_t cap = bnz_max_compressed_size(in_len) + 64;
         if (ctx->out_big_cap < cap) {             // (kept across calls: its pages stay faulted in)
             free(ctx->out_big);

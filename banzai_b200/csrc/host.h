@@ -80,6 +80,7 @@ struct Device {
     cudaStream_t stream3[3] = {};       // low-priority streams: MTF of finished blocks fills the sort's tail
     // arenas (grown on demand, kept across calls)
     DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, ws_hist;
+    DevBuf v_marks, v_lfl, v_flags;     // self-verification (verify.cu)
     DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, ch_tiles, rle_blocks, crc_acc;
     DevBuf seg_base, seg_list, seg_cnt, seg_state, num_names, syms, sym_off, sym_len, freqs, mtf_ids, mtf_cseg;
     DevBuf lens, codes, tf, num_tables, num_sel, span_base, hdr, hdr_bits, crc, blk_bits, blk_bitoff,
@@ -103,7 +104,7 @@ struct bnz_ctx {
     int ctas_per_sm = 0;
     int bwt_cluster = -1;         // CTAs per bzip2 block (-1: auto, 0/1: single-CTA kernel)
     int bwt_threads = 512;
-    int bwt_cluster_below = 400;       // auto mode: cluster kernel when a device gets fewer blocks than this
+    int bwt_cluster_below = 250;       // auto mode: cluster kernel when a device gets fewer blocks than this
     // cached pinned output buffer handed to the caller by bnz_encode / returned by bnz_free
     uint8_t *out_cache = nullptr;
     size_t out_cache_cap = 0;
@@ -119,6 +120,11 @@ struct bnz_ctx {
     int piece_blocks_per_sm_x16 = 17;  // size of the first piece in blocks per SM (x 1/16)
     int h2d_overlap = 1;               // one device, host input: upload in two pieces, sort the first while the second arrives
     int crc_low_prio = 1;              // block CRCs on the low-priority stream (they would delay the start of the sort)
+    // where the shards of the current bnz_encode call may be downloaded as soon as their bit phase is
+    // known (several devices, one batch); o == nullptr: the caller packs and downloads afterwards
+    struct { uint8_t *o = nullptr; size_t cap = 0; } early_out;
+    int verify = 0;                    // check every block on the device (and the CRCs on the host) before emitting
+    int verify_corrupt = 0;            // test hook: damage an intermediate of block 0 behind the sort's back
     int reuse_input = 0;               // the caller re-encodes the SAME host buffer: keep its device copy resident (benchmarks)
     int mtf_groups = 2;
     int mtf_overlap = 70;              // percent of a device's blocks whose MTF may run beside the sort (0: off)
@@ -182,7 +188,8 @@ struct Batch {                      // host description of the blocks resident o
 
 int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt, const uint64_t *d_blk_off,
                    const uint32_t *d_blk_len, uint32_t n_blocks, uint32_t max_len, uint32_t *d_ptr,
-                   uint8_t *d_has_byte, BwtStats *d_stats, uint32_t *d_done = nullptr, bool *done_armed = nullptr);
+                   uint8_t *d_has_byte, BwtStats *d_stats, uint32_t *d_done = nullptr, bool *done_armed = nullptr,
+                   uint32_t *d_marks = nullptr);
 int rle_plan(bnz_ctx *ctx, Device &d, const uint8_t *d_in, const uint8_t *h_in, uint64_t N, int level,
              std::vector<RleBlock> &blocks, bool final = true, uint64_t *consumed = nullptr);
 int rle_emit_shard(bnz_ctx *ctx, Device &d, const uint8_t *in_base, uint64_t N, const uint64_t *oin_base,
@@ -204,6 +211,7 @@ struct Shard {
     Device *d = nullptr;
     std::vector<RleBlock> blocks;      // rle_off rebased to this device's rle buffer
     std::vector<uint32_t> crcs;
+    std::vector<uint32_t> vflags;      // verify: per block VERIFY_BAD_* bits
     std::vector<BwtStats> bst;
     Batch bt;
     HuffArgs ha;
@@ -212,6 +220,9 @@ struct Shard {
     int rc = BNZ_OK;
     std::string err;
     uint64_t h2d_bytes = 0;            // input bytes this shard's device received
+    bool packed = false;               // already packed at its bit phase and copied to the host (sharded path)
+    uint32_t first_word = 0;           // its first 32-bit word, when that word is shared with the previous shard
+    size_t d2h_bytes = 0;
     Shard() = default;
     Shard(const Shard &o) { d = o.d; }
 };

@@ -86,6 +86,7 @@ struct BwtArgs {
     uint32_t *ws_hist;            // one-CTA kernel: per CTA BWT_HIST_WORDS words (per-pass digit histograms)
     void *ws_ctl;                 // cluster kernel only: per cluster BWT_CTL_BYTES of control state
     uint32_t *done;               // optional [n_blocks], host-mapped: set to 1 (release.sys) when a block's outputs are complete
+    uint32_t *marks;              // optional [n_blocks][VERIFY_MARKS]: row (sorted position) of the rotations 0, 4096, 8192, ... (verify.cu)
 };
 
 size_t bwt_smem_bytes();
@@ -95,6 +96,29 @@ cudaError_t bwt_launch(const BwtArgs &a, int grid, cudaStream_t stream);
 size_t bwtc_smem_bytes(int threads);
 cudaError_t bwtc_max_clusters(int threads, int C, int *n_clusters);
 cudaError_t bwtc_launch(const BwtArgs &a, int threads, int C, int n_clusters, cudaStream_t stream);
+
+// ---------------------------------------------------------------- self-verification (verify.cu)
+
+#define VERIFY_SPACING 4096       /* text positions per backward walk */
+#define VERIFY_MARKS 224          /* >= ceil(900000 / VERIFY_SPACING) + 1 */
+#define VERIFY_BAD_RLE 1u
+#define VERIFY_BAD_BWT 2u
+struct VerifyArgs {
+    const uint8_t *in_base;       // input bytes, indexed by GLOBAL input position
+    uint8_t *rle;                 // RLE1 images (block b at rle + blocks[b].rle_off == rle + blk_off[b])
+    uint8_t *bwt;                 // BWT bytes, same layout
+    uint32_t *ptr;                // [n_blocks] origPtr
+    const uint64_t *blk_off;
+    const uint32_t *blk_len;
+    const RleBlock *blocks;       // [n_blocks] as cut by the host walk
+    uint32_t n_blocks;
+    uint32_t *lfl;                // scratch: one word per byte of the rle buffer
+    const uint32_t *marks;        // [n_blocks][VERIFY_MARKS] from the sort kernel
+    const BwtStats *stats;        // [n_blocks] (tied flag)
+    uint32_t *flags;              // [n_blocks] out: VERIFY_BAD_* (zeroed by the host)
+    int corrupt;                  // test hook: 1 flip a BWT byte, 2 shift origPtr, 3 flip an RLE1 byte (block 0)
+};
+cudaError_t verify_launch(const VerifyArgs &a, cudaStream_t st, uint32_t *launches);
 
 // ---------------------------------------------------------------- K5 MTF + RLE2 (mtf.cu)
 

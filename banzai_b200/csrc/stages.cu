@@ -10,7 +10,7 @@
 int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt,
                           const uint64_t *d_blk_off, const uint32_t *d_blk_len, uint32_t n_blocks,
                           uint32_t max_len, uint32_t *d_ptr, uint8_t *d_has_byte, BwtStats *d_stats,
-                          uint32_t *d_done, bool *done_armed)
+                          uint32_t *d_done, bool *done_armed, uint32_t *d_marks)
 {
     if (done_armed) *done_armed = false;
     if (n_blocks == 0) return BNZ_OK;
@@ -29,10 +29,11 @@ int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt
     a.ws_ctl = nullptr;
     a.ws_hist = nullptr;
     a.done = nullptr;
+    a.marks = d_marks;
 
     // auto: many blocks -> one persistent CTA per block (best aggregate throughput);
     // few blocks -> one cluster per block so that every SM has work and the randomly accessed
-    // arrays stay in L2 (measured crossover ~400 blocks per device, tools/bwt_blocks_sweep.py)
+    // arrays stay in L2 (measured crossover ~250 blocks per device, tools/bwt_blocks_sweep.py)
     int C = ctx->bwt_cluster;
     if (C < 0) C = (n_blocks >= (uint32_t)ctx->bwt_cluster_below) ? 0 : (n_blocks <= 40 ? 16 : 8);
     if (C > 1) {

@@ -32,7 +32,8 @@ enum {
     BNZ_ECUDA = 2,      /* CUDA runtime / driver error, or no usable device */
     BNZ_ENOMEM = 3,     /* host or device allocation failed */
     BNZ_EINTERNAL = 4,  /* internal invariant violated (reference: assert!/panic! sites) */
-    BNZ_EIO = 5         /* a sink callback or a file operation failed (reference: io::Error via `?`) */
+    BNZ_EIO = 5,        /* a sink callback or a file operation failed (reference: io::Error via `?`) */
+    BNZ_EVERIFY = 6     /* "verify": a block failed the self-check; nothing was emitted */
 };
 
 /* ---- context -------------------------------------------------------------------------
@@ -51,9 +52,15 @@ BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
 
 /* tunables (call before encoding). keys:
  *   "bwt_cluster"        -1 auto | 0 one CTA per block | 2..16 CTAs (one cluster) per block
- *   "bwt_cluster_below"  auto mode: cluster kernel when a device gets fewer blocks than this
+ *   "bwt_cluster_below"  auto mode: cluster kernel when a device gets fewer blocks than this (250)
  *   "bwt_threads"        512 | 1024, cluster kernel
  *   "bwt_ctas_per_sm"    0 = auto
+ *   "verify"             1: self-verification (the reference has no decoder, README.md:9; its safety
+ *                        net is the libbz2 round trip of fuzz/fuzz_targets/round_trip.rs): before a
+ *                        stream is returned, every block's RLE1 image is decoded back to its input
+ *                        bytes and its (BWT, origPtr) is inverted back to the RLE1 image on the
+ *                        device, and the cut chain and the block CRCs are re-derived on the host;
+ *                        BNZ_EVERIFY on any mismatch.  Covers RLE1, BWT and CRC, not the entropy stage.
  *   "reuse_input"        1: the caller encodes the SAME host buffer again and again (benchmarks);
  *                        every device keeps its copy of the input resident, the next call of the
  *                        identical (pointer, length) skips the upload

@@ -1,10 +1,11 @@
+"""one-CTA-per-block kernel vs cluster kernel by number of blocks on the device (mixed corpus, level 9)"""
 import sys, os
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import corpus, banzai_b200
 blk = 899999
 data = corpus.mixed(600 * blk)
 ctx = banzai_b200.Context(n_gpus=1)
-for nb in (12, 37, 74, 148, 296, 600):
+for nb in (12, 37, 74, 137, 148, 200, 296, 400, 600):
     blocks = [data[i * blk:(i + 1) * blk] for i in range(nb)]
     res = []
     for clu in (0, 4, 8, 16):
