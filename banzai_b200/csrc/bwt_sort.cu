@@ -28,10 +28,14 @@
 //             [ rank : rank[idx+h] : idx ] are written out and sorted by the 20 bits of
 //             rank[idx+h] with the radix passes of round 0 (the passes whose digit is the same in
 //             every record are skipped: three instead of five).
-//   rank[] is updated in place while a round runs.  A group's ranks are all replaced between
-//   two CTA barriers and no group is read (as rank[idx+h]) and written in the same phase, so a
-//   reader sees every group either completely refined or not at all — both are consistent
-//   with the final order, the refined one merely carries more information.
+//   Rank stores: round 0 writes all n ranks; scattered as 4-byte stores they cost a 32-byte DRAM
+//   sector read + write each, and with 296 CTAs doing so at once the kernel was bound by exactly
+//   that.  Its ranks therefore go through apply_ranks_bucketed (one more radix pass by idx >> 13,
+//   then rank[] is written chunk by chunk with coalesced stores).  Later rounds store ranks at once:
+//   all ranks of a tile's groups are replaced between two CTA barriers and nothing is gathered
+//   meanwhile, so a reader sees a group either completely refined or not at all — both are
+//   consistent with the final order, the refined one merely carries more information, which
+//   saves record-rounds (measured: 3.03 against 3.17 per byte on the mixed corpus).
 //   A round that splits no group proves the remaining groups are identical rotations
 //   (period | n); their positions inside the group are arbitrary for the BWT bytes and
 //   origPtr = group base + group size - 1.
@@ -59,6 +63,8 @@ constexpr u32 RANK_MASK = (1u << 20) - 1u;
 constexpr u32 DONE = 0x80000000u;
 constexpr int MAX_ROUNDS = 48;
 constexpr int BMW = TILE / 32;       // words of a per-tile bitmap
+constexpr int UPD_SHIFT = 13;        // round-0 rank updates are bucketed by idx >> 13 ...
+constexpr u32 UPD_CHUNK = 1u << UPD_SHIFT;   // ... so that a bucket covers 8192 ranks = 32 KB of rank[]
 static_assert(WORDS <= T && BMW == 128 && NW == 16, "scan layouts below assume 512 threads, 4096-record tiles");
 
 struct __align__(128) Smem {
@@ -90,6 +96,18 @@ enum { ACC_ACTIVE = 0, ACC_PASSES, ACC_TILE, ACC_CYC_BUILD, ACC_CYC_RADIX, ACC_C
 __device__ __forceinline__ u32 *hist_of(Smem &sm) { return reinterpret_cast<u32 *>(sm.buf1); }
 
 __device__ __forceinline__ u32 digit_of(u64 rec, int pass) { return (u32)(rec >> (IDX_BITS + pass * BITS)) & (u32)(BINS - 1); }
+
+// update record of the deferred rank scatter: [ done:1 rank:20 | idx >> 13 : 8 | 0:7 | idx & 8191 : 13 ]
+__device__ __forceinline__ u64 upd_record(u32 nr, bool done, u32 id)
+{
+    const u64 val = (u64)nr | (done ? (1ull << 20) : 0ull);
+    return (val << 28) | ((u64)(id >> UPD_SHIFT) << IDX_BITS) | (id & (UPD_CHUNK - 1));
+}
+__device__ __forceinline__ u32 upd_rank_word(u64 e)
+{
+    const u32 val = (u32)(e >> 28);
+    return (val & RANK_MASK) | ((val >> 20) ? DONE : 0u);
+}
 
 __device__ __forceinline__ u32 lanemask_le()
 {
@@ -391,7 +409,10 @@ struct RerankOut {
 // Walk records sorted by their 40-bit key (round 0: all of the block, `initial`; later: one group
 // that went through the global passes), assign new ranks, retire singletons, and append the
 // records that stay active to the active list at list[out_pos ...] IN SORTED ORDER.
-__device__ RerankOut rerank(Smem &sm, const u64 *src, u32 count, bool initial, u32 *rank, u64 *list, u32 out_pos)
+// `upd` != nullptr (round 0): instead of scattering the ranks, write one update record per rotation
+// (upd[j] for the j-th sorted record) for apply_ranks_bucketed.
+__device__ RerankOut rerank(Smem &sm, const u64 *src, u32 count, bool initial, u32 *rank, u64 *list, u32 out_pos,
+                            u64 *upd = nullptr)
 {
     const u32 tid = threadIdx.x;
     u32 carry_grp = 0, carry_key = 0;       // 1-based positions of the latest heads so far
@@ -463,14 +484,24 @@ __device__ RerankOut rerank(Smem &sm, const u64 *src, u32 count, bool initial, u
             if ((flg[k] & 3u) == 1u) st_stream(list + at++, ((u64)nrv[k] << IDX_BITS) | idx[k]);
         }
         n_active += tot_a;
+        if (upd) {
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            if (flg[k] & 1u) {
-                const u32 id = idx[k];
-                if (flg[k] & 2u) {
-                    st_keep(rank + id, nrv[k] | DONE);
-                } else if (!(flg[k] & 4u)) {
-                    st_keep(rank + id, nrv[k]);
+            for (int k = 0; k < K; k++) {
+                if (flg[k] & 1u) {
+                    const u32 id = idx[k];
+                    st_stream(upd + j0 + k, upd_record(nrv[k], (flg[k] & 2u) != 0, id));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (flg[k] & 1u) {
+                    const u32 id = idx[k];
+                    if (flg[k] & 2u) {
+                        st_keep(rank + id, nrv[k] | DONE);
+                    } else if (!(flg[k] & 4u)) {
+                        st_keep(rank + id, nrv[k]);
+                    }
                 }
             }
         }
@@ -481,6 +512,44 @@ __device__ RerankOut rerank(Smem &sm, const u64 *src, u32 count, bool initial, u
     o.active = n_active;                     // (block-uniform: sum of the tile totals)
     o.splits = block_sum<T>(n_split, sm.scratch);
     return o;
+}
+
+// The ranks of round 0 reach rank[] without random DRAM accesses.  rerank left one update record
+// per rotation, in sorted order; one radix pass by idx >> 13 groups them by 32 KB chunk of rank[]
+// (every bucket holds exactly the 8192 positions of its chunk, so its histogram is known in
+// advance), and every chunk is then assembled in shared memory and written out with coalesced
+// stores.  36 bytes of streaming traffic per rotation instead of a 32-byte sector read + write:
+// with all CTAs scattering 4-byte ranks at once the kernel was bound by exactly those sectors
+// (profiles/README.md; doing the same in the later rounds costs their in-place refinement and
+// measured slower on the mixed corpus).
+__device__ void apply_ranks_bucketed(Smem &sm, u64 *upd, u64 *tmp, u32 n, u32 *rank, u32 *ghist, u32 &phase)
+{
+    const u32 tid = threadIdx.x;
+    for (int b = tid; b < BINS; b += T) {
+        const u32 lo = (u32)b << UPD_SHIFT;
+        ghist[b] = lo < n ? min(UPD_CHUNK, n - lo) : 0u;        // bucket b lives at tmp[8192 b ...]
+    }
+    __syncthreads();
+    radix_pass(sm, upd, tmp, n, 0, ghist, phase);
+    u32 *chunk = reinterpret_cast<u32 *>(sm.buf0);              // 8192 ranks
+    for (u32 lo = 0; lo < n; lo += UPD_CHUNK) {
+        const u32 len = min(UPD_CHUNK, n - lo);
+#pragma unroll
+        for (int k = 0; k < 2 * K; k++) {
+            const u32 j = k * T + tid;
+            if (j < len) {
+                const u64 e = ld_stream64(tmp + lo + j);
+                chunk[(u32)e & (UPD_CHUNK - 1)] = upd_rank_word(e);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 2 * K; k++) {
+            const u32 j = k * T + tid;
+            if (j < len) st_keep(rank + lo + j, chunk[j]);
+        }
+        __syncthreads();
+    }
 }
 
 // One tile of the active list: the whole groups among list[p .. p+TILE), sorted by rank[idx + h]
@@ -691,13 +760,9 @@ __device__ u32 refine_tile(Smem &sm, u64 *list, u32 p, u32 count, u32 hm, u32 n,
                 n_active += __popc(abw);
                 n_split += __popc(kbw & ~gbw);
             }
-            if (valid) {
-                if (single) st_keep(rank + id, nr | DONE);
-                else {
-                    if (nr != r1) st_keep(rank + id, nr);        // (the first subgroup keeps its rank)
-                    spare[q] = ((u64)nr << IDX_BITS) | id;
-                }
-            }
+            // rank stores: singletons are final, the first subgroup of a group keeps its rank
+            if (valid && (single || nr != r1)) st_keep(rank + id, nr | (single ? DONE : 0u));
+            if (active) spare[q] = ((u64)nr << IDX_BITS) | id;
         } else if (lane == 0) {
             sm.bm_a[w * K + k] = 0;
         }
@@ -872,9 +937,11 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
             acc(ACC_CYC_BUILD, (u64)(clock64() - c0));
             const u64 *sorted = sort_keys(n);
             c0 = clock64();
-            RerankOut ro = rerank(sm, sorted, n, true, rank, list, 0);
+            u64 *upd = (sorted == bufC) ? bufD : bufC;             // the pass buffer that is free
+            RerankOut ro = rerank(sm, sorted, n, true, rank, list, 0, upd);
             count = ro.active;
             __syncthreads();
+            apply_ranks_bucketed(sm, upd, const_cast<u64 *>(sorted), n, rank, ghist, phase);
             acc(ACC_CYC_RERANK, (u64)(clock64() - c0));
         }
 

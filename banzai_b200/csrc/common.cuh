@@ -194,6 +194,16 @@ __device__ __forceinline__ void st_stream(u64 *p, u64 v)
     *p = v;
 #endif
 }
+__device__ __forceinline__ u64 ld_stream64(const u64 *p)    // read once: do not displace the randomly accessed arrays
+{
+#if BWT_L2HINT >= 1
+    u64 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(L2_EVICT_FIRST) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
 __device__ __forceinline__ u32 ld_keep(const u32 *p)
 {
 #if BWT_L2HINT >= 2

@@ -61,7 +61,7 @@ int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt
     if (per_sm <= 0) return fail(ctx, BNZ_ECUDA, "bwt kernel does not fit on an SM");
     if (ctx->ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->ctas_per_sm);
     int grid = (int)std::min<uint64_t>((uint64_t)n_blocks, (uint64_t)d.sm_count * per_sm);
-    size_t stride = ((size_t)max_len + 15) & ~(size_t)15;
+    size_t stride = ((size_t)max_len + 8191) & ~(size_t)8191;    // whole 8192-record buckets (apply_ranks_bucketed)
     CK(ctx, d.ws_rec.ensure((size_t)grid * 3 * stride * sizeof(uint64_t)));
     CK(ctx, d.ws_rank.ensure((size_t)grid * stride * sizeof(uint32_t)));
     CK(ctx, d.ws_hist.ensure((size_t)grid * BWT_HIST_WORDS * 4));

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out/c10
+( time timeout 900 python -m pytest tests/test_bwt_gpu.py -x -q ) > gpurun_out/c10/pytest_bwt.log 2>&1
+tail -4 gpurun_out/c10/pytest_bwt.log
+for k in text mixed; do timeout 300 python tools/bwt_perf.py $k 296 9 0 2>&1 | tail -1; done | tee gpurun_out/c10/perf.log
+timeout 300 python tools/bwt_perf.py mixed 600 9 0 2>&1 | tail -1 | tee -a gpurun_out/c10/perf.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/c10/bench1.json 2> gpurun_out/c10/bench1.err
+python - <<'PY'
+import json
+l=json.loads(open('gpurun_out/c10/bench1.json').read().strip().splitlines()[-1])
+print({k:l[k] for k in ('value','ms_per_step','stage_ms','parity_check')}, l['e2e'], l['roofline'])
+PY
+tail -3 gpurun_out/c10/bench1.err

@@ -72,7 +72,7 @@ if os.path.exists(rep):
         d["mixed-1GiB-L9"] = int(traffic)
         d["_source"] = f"profiles/{tag}_bwt_sort_ncu.csv (ncu --set full, one launch, bench workload)"
         json.dump(d, open(tj, "w"), indent=1)
-    lines = subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_lines.py"), rep, "bwt_sort_kernelILi8",
+    lines = subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_lines.py"), rep, "bwt_sort_kernel",
                             os.path.join(root, "banzai_b200", "csrc", "bwt_sort.cu"), "40"],
                            capture_output=True, text=True).stdout
     open(os.path.join(pr, f"{tag}_bwt_sort_stalls_by_line.txt"), "w").write(
