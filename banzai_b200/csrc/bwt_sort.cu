@@ -411,8 +411,10 @@ struct RerankOut {
 // records that stay active to the active list at list[out_pos ...] IN SORTED ORDER.
 // `upd` != nullptr (round 0): instead of scattering the ranks, write one update record per rotation
 // (upd[j] for the j-th sorted record) for apply_ranks_bucketed.
+// (m_val, m_cnt): the group has m_cnt further members whose rank[idx+h] is m_val; they are not among the
+// records (refine_majority) but take their places in the numbering.
 __device__ RerankOut rerank(Smem &sm, const u64 *src, u32 count, bool initial, u32 *rank, u64 *list, u32 out_pos,
-                            u64 *upd = nullptr)
+                            u64 *upd = nullptr, u32 m_val = 0xffffffffu, u32 m_cnt = 0)
 {
     const u32 tid = threadIdx.x;
     u32 carry_grp = 0, carry_key = 0;       // 1-based positions of the latest heads so far
@@ -466,7 +468,7 @@ __device__ RerankOut rerank(Smem &sm, const u64 *src, u32 count, bool initial, u
                 bool hk = (pk[k] == j + 1);
                 bool hg = (pg[k] == j + 1);
                 u32 r1 = initial ? 0u : (u32)(key[k + 1] >> 20) & RANK_MASK;
-                nrv[k] = r1 + (p_key - p_grp);
+                nrv[k] = r1 + (p_key - p_grp) + ((((u32)key[k + 1] & RANK_MASK) > m_val) ? m_cnt : 0u);
                 bool single = hk && (j + 1 == count || key[k + 2] != key[k + 1]);
                 flg[k] = 1u | (single ? 2u : 0u);
                 // a record that stays in the first subgroup of its old group keeps its rank: its
@@ -551,6 +553,9 @@ __device__ void apply_ranks_bucketed(Smem &sm, u64 *upd, u64 *tmp, u32 n, u32 *r
         __syncthreads();
     }
 }
+
+__device__ __forceinline__ void tile_finish(Smem &sm, u64 (&rec)[K], u32 nrows, u32 tile_n, u32 G, u64 *list, u32 *rank,
+                                            u32 &out_pos, u32 &n_active, u32 &n_split, u32 m_val, u32 m_cnt);
 
 // One tile of the active list: the whole groups among list[p .. p+TILE), sorted by rank[idx + h]
 // inside shared memory.  Returns the number of list records consumed; 0 = the group that starts at
@@ -647,6 +652,21 @@ __device__ u32 refine_tile(Smem &sm, u64 *list, u32 p, u32 count, u32 hm, u32 n,
         }
     }
 
+    tile_finish(sm, rec, nrows, tile_n, G, list, rank, out_pos, n_active, n_split, 0xffffffffu, 0u);
+    return tile_n;
+}
+
+// Second half of a tile: `rec` holds the sort items [ group:12 | rank[idx+h]:20 | idx:20 ] of the
+// tile positions w*256 + 32k + lane (~0 beyond tile_n), sm.r1tab the rank of every group.
+// Sorts them in shared memory, derives the new ranks, stores the changed ones, and writes the
+// records that stay active to list[out_pos ...].  (m_val, m_cnt): the group also has m_cnt members
+// whose rank[idx+h] is m_val; they are not in the tile (refine_majority) but take their places in
+// the numbering, between the items below and the items above m_val.
+__device__ __forceinline__ void tile_finish(Smem &sm, u64 (&rec)[K], u32 nrows, u32 tile_n, u32 G, u64 *list, u32 *rank,
+                                            u32 &out_pos, u32 &n_active, u32 &n_split, u32 m_val, u32 m_cnt)
+{
+    const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    const u32 q0 = w * (K * 32) + lane;
     // ---- stable LSD radix sort of the tile in shared memory (20 + log2(G) key bits)
     const int npass = (G <= 16) ? 3 : 4;
     u64 *fin = nullptr;
@@ -747,7 +767,7 @@ __device__ u32 refine_tile(Smem &sm, u64 *list, u32 p, u32 count, u32 hm, u32 n,
             const u32 g = (u32)(it >> (IDX_BITS + 20)) & 0xfffu;
             const u32 id = (u32)it & IDX_MASK;
             const u32 r1 = valid ? sm.r1tab[g] : 0u;
-            const u32 nr = r1 + (pk - pg);
+            const u32 nr = r1 + (pk - pg) + ((((u32)(it >> IDX_BITS) & RANK_MASK) > m_val) ? m_cnt : 0u);
             const bool khead = (kbw >> lane) & 1u;
             u32 nxt;                                              // is position q + 1 a key head (or the end)?
             if (lane < 31) nxt = (kbw >> (lane + 1)) & 1u;
@@ -793,7 +813,6 @@ __device__ u32 refine_tile(Smem &sm, u64 *list, u32 p, u32 count, u32 hm, u32 n,
     }
     out_pos += sm.s_tot;
     __syncthreads();
-    return tile_n;
 }
 
 // first position > p + TILE of the active list whose rank differs from r1p (the list is sorted
@@ -825,6 +844,173 @@ __device__ u32 group_end(Smem &sm, const u64 *list, u32 p, u32 count, u32 r1p)
         }
     }
     return a;
+}
+
+// A group larger than a tile in which (nearly) every member has the same rank[idx + h] = M: the
+// signature of periodic data, where a group of ~n/period rotations loses only the few members
+// within h of the point where the period breaks per round (the reference's SA-IS has no such
+// worst case, README.md:7; plain doubling pays 17 rounds of full-group sorts for it).  Sorting is
+// then a three-way split: the members equal to M keep their order and stay one group, and the
+// <= 4096 others are sorted as one tile.  Two streaming passes over the group (one gather each
+// way) instead of key build + three radix passes + re-rank.  Returns 0 (nothing done) if the group
+// does not have that shape, 1 if it is done, 2 if the members equal to M are done and the others
+// (more than a tile, at most half of the group) wait in outl[0 .. *n_others) as key records for the
+// global passes; *m_val = M, *m_cnt = members equal to M.
+__device__ int refine_majority(Smem &sm, u64 *list, u32 p, u32 m, u32 hm, u32 n, u32 *rank, u64 *outl, u32 *bitmap,
+                               u32 &out_pos, u32 &n_active, u32 &n_split, u32 *m_val, u32 *m_cnt, u32 *n_others)
+{
+    const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    const u32 r1 = (u32)(list[p] >> IDX_BITS) & RANK_MASK;
+    // ---- M from 32 samples; give up unless most of them agree
+    if (w == 0) {
+        const u32 j = p + (u32)(((u64)m * (2 * lane + 1)) >> 6);
+        u32 q = ((u32)list[j] & IDX_MASK) + hm;
+        if (q >= n) q -= n;
+        const u32 r2 = ld_keep(rank + q) & RANK_MASK;
+        const u32 mv = __shfl_sync(0xffffffffu, r2, 16);
+        const u32 agree = __popc(__ballot_sync(0xffffffffu, r2 == mv));
+        if (lane == 0) {
+            sm.wcnt[0] = mv;
+            sm.wcnt[1] = agree;
+            sm.s_tot = 0;                                    // members that differ from M, appended to outl
+        }
+    }
+    __syncthreads();
+    const u32 M = sm.wcnt[0];
+    if (sm.wcnt[1] < 28) return 0;                           // (block-uniform)
+
+    // ---- pass A: classify; the members that differ from M go to outl[], one bit per member to bitmap[]
+    u32 n_lt = 0;
+    for (u32 base = 0; base < m; base += TILE) {
+        u64 rec[K];
+        u32 r2[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 j = base + w * (K * 32) + k * 32 + lane;
+            rec[k] = (j < m) ? list[p + j] : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 j = base + w * (K * 32) + k * 32 + lane;
+            r2[k] = M;
+            if (j < m) {
+                u32 q = ((u32)rec[k] & IDX_MASK) + hm;
+                if (q >= n) q -= n;
+                r2[k] = ld_keep(rank + q) & RANK_MASK;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 j = base + w * (K * 32) + k * 32 + lane;
+            const bool odd = r2[k] != M;                     // (never for j >= m)
+            const u32 ob = __ballot_sync(0xffffffffu, odd);
+            if (base + w * (K * 32) + k * 32 < m) {          // (warp-uniform)
+                if (lane == 0) bitmap[(base + w * (K * 32) + k * 32) >> 5] = ob;
+                if (ob) {
+                    u32 at = 0;
+                    if (lane == 0) at = atomicAdd(&sm.s_tot, (u32)__popc(ob));
+                    at = __shfl_sync(0xffffffffu, at, 0) + __popc(ob & lanemask_lt());
+                    if (odd) outl[at] = ((u64)r1 << (IDX_BITS + 20)) | ((u64)r2[k] << IDX_BITS) | ((u32)rec[k] & IDX_MASK);
+                    if (odd && r2[k] < M) n_lt++;
+                }
+            }
+            (void)j;
+        }
+    }
+    n_lt = block_sum<T>(n_lt, sm.scratch);                   // (ends with barriers: s_tot, outl and bitmap are complete)
+    const u32 n_out = sm.s_tot;
+    __syncthreads();
+    if (n_out > (u32)TILE && (u64)n_out * 2 > m) return 0;   // (nothing but scratch was written so far)
+    const u32 n_eq = m - n_out;
+    *m_val = M;
+    *m_cnt = n_eq;
+    *n_others = n_out;
+    const u32 nr_eq = r1 + n_lt;
+    const bool eq_single = n_eq == 1;
+
+    // ---- pass C: the members equal to M, in their old order, to the front of the group's place in the
+    // list (in place: a tile is read completely before anything of it is written, and nothing moves right)
+    if (n_eq > 0) {
+        u32 done_eq = 0;
+        for (u32 base = 0; base < m; base += TILE) {
+            u64 rec[K];
+            u32 eb[K];
+            u32 cnt = 0;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const u32 row = base + w * (K * 32) + k * 32;
+                const u32 j = row + lane;
+                rec[k] = (j < m) ? list[p + j] : 0ull;
+                u32 ob = (row < m) ? bitmap[row >> 5] : 0xffffffffu;
+                if (row + 32 > m && row < m) ob |= ~((1u << (m - row)) - 1u);        // beyond the group: not a member
+                eb[k] = ~ob;
+                cnt += __popc(eb[k]);
+            }
+            if (lane == 0) sm.wcnt[w] = cnt;
+            __syncthreads();
+            u32 woff = 0, total = 0;
+#pragma unroll
+            for (int v = 0; v < NW; v++) {
+                const u32 c = sm.wcnt[v];
+                if ((u32)v < w) woff += c;
+                total += c;
+            }
+            u32 rowbase = out_pos + done_eq + woff;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if ((eb[k] >> lane) & 1u) {
+                    const u32 id = (u32)rec[k] & IDX_MASK;
+                    if (!eq_single) st_stream(list + rowbase + __popc(eb[k] & lanemask_lt()), ((u64)nr_eq << IDX_BITS) | id);
+                    if (eq_single || nr_eq != r1) st_keep(rank + id, nr_eq | (eq_single ? DONE : 0u));
+                }
+                rowbase += __popc(eb[k]);
+            }
+            done_eq += total;
+            __syncthreads();
+        }
+        if (!eq_single) {
+            out_pos += n_eq;
+            if (tid == 0) n_active += n_eq;
+        }
+    }
+
+    if (n_out > (u32)TILE) {
+        if (tid == 0 && n_eq > 0) n_split++;                 // the members equal to M split from the others
+        return 2;
+    }
+    // ---- the others: one tile, sorted in shared memory, numbered around the members equal to M
+    if (n_out > 0) {
+        u64 rec[K];
+        const u32 nrows = (n_out > w * (K * 32)) ? min((u32)K, (n_out - w * (K * 32) + 31) / 32) : 0u;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 q = w * (K * 32) + k * 32 + lane;
+            rec[k] = (q < n_out) ? (outl[q] & ((1ull << (IDX_BITS + 20)) - 1ull)) : ~0ull;      // group number 0
+        }
+        if (tid == 0) {
+            sm.r1tab[0] = r1;
+            if (n_eq > 0) n_split++;                         // the members equal to M split from the others
+        }
+        __syncthreads();
+        tile_finish(sm, rec, nrows, n_out, 1, list, rank, out_pos, n_active, n_split, M, n_eq);
+    }
+    return 1;
+}
+
+// digit histograms of key records that are already in place (the others of refine_majority)
+__device__ void hist_records(Smem &sm, const u64 *recs, u32 cnt)
+{
+    hist_clear(sm);
+    for (u32 base = 0; base < cnt; base += TILE) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 j = base + k * T + threadIdx.x;
+            if (j < cnt) hist_add(sm, recs[j]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sm.s_count = cnt;
+    __syncthreads();
 }
 
 // Remaining groups are sets of identical rotations: give them distinct positions inside
@@ -964,11 +1150,25 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
                 // a group larger than a tile: sort it by rank[idx + h] through HBM
                 const u32 ge = group_end(sm, list, p, count, (u32)(list[p] >> IDX_BITS) & RANK_MASK);
                 const u32 m = ge - p;
-                build_group(sm, rank, n, hm, list + p, m, bufC);
+                u32 m_val = 0xffffffffu, m_cnt = 0, n_keys = m;
+                const int how = refine_majority(sm, list, p, m, hm, n, rank, bufC, reinterpret_cast<u32 *>(bufD), out_pos, n_act,
+                                                n_spl, &m_val, &m_cnt, &n_keys);
+                if (how == 1) {
+                    acc(ACC_TILE, m);
+                    acc(ACC_CYC_TILE, (u64)(clock64() - c0));
+                    p = ge;
+                    continue;
+                }
+                if (how == 2) {
+                    acc(ACC_TILE, m_cnt);
+                    hist_records(sm, bufC, n_keys);          // (the other members are in bufC already)
+                } else {
+                    build_group(sm, rank, n, hm, list + p, m, bufC);
+                }
                 acc(ACC_CYC_BUILD, (u64)(clock64() - c0));
-                const u64 *srt = sort_keys(m);
+                const u64 *srt = sort_keys(n_keys);
                 c0 = clock64();
-                RerankOut rg = rerank(sm, srt, m, false, rank, list, out_pos);
+                RerankOut rg = rerank(sm, srt, n_keys, false, rank, list, out_pos, nullptr, m_val, m_cnt);
                 out_pos += rg.active;
                 big_spl += rg.splits;
                 __syncthreads();
