@@ -652,6 +652,15 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) bwt_cluster_kernel(BwtA
             st.cyc_rerank = (u64)cyc_rerank;
             a.stats[blk] = st;
         }
+        if (a.done) {
+            // every CTA's stores of this block precede the cluster barrier; publish them, then raise the
+            // block's flag (host-mapped memory: the host queues the MTF of finished blocks beside the sort)
+            cluster.sync();
+            if (c == 0 && tid == 0) {
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.done + blk), "r"(1u) : "memory");
+            }
+        }
         __syncthreads();
     }
 }

@@ -229,14 +229,13 @@ struct Shard {
 
 // K1 emit .. K7 + headers for one shard; ends with a host sync that yields block_bits.
 
-// SURVEY §8(d) algorithmic bytes of the BWT sort, per record and round:
-//   sorted through HBM : 16 per radix pass executed (read + write of the 8-byte record) + 36
-//                        (8 histogram/key write, 8 + 4 re-rank read + rank write, 4 + 4 rank gathers, 8 list record)
-//   sorted in shared memory: 24 (8 list read, 4 rank gather, 4 rank write, 8 list write)
-// plus 9 per byte of the block (text read, initial 8-byte key).
+// SURVEY §8(d) algorithmic bytes of the BWT sort: 9 per byte of the block (text read, initial 8-byte
+// key) + per record and round 16 per radix pass through HBM (read + write of the 8-byte record;
+// P_r = 0 for a record that is sorted inside shared memory) + 36 (key/list record write and read,
+// the rank gathers, the rank write).
 inline uint64_t bwt_algorithmic_bytes(const bnz_stats &s)
 {
-    return 9 * s.bwt_n + 16 * s.bwt_sum_active_passes + 36 * (s.bwt_sum_active - s.bwt_sum_tile) + 24 * s.bwt_sum_tile;
+    return 9 * s.bwt_n + 16 * s.bwt_sum_active_passes + 36 * s.bwt_sum_active;
 }
 
 void put_bits_host(uint8_t *buf, uint64_t bitpos, uint64_t value, int nbits);      // MSB first

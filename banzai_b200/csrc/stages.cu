@@ -51,6 +51,10 @@ int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt
         a.ws_rank = d.ws_rank.as<uint32_t>();
         a.ws_stride = stride;
         a.ws_ctl = d.ws_ctl.p;
+        if (d_done && n_blocks > (uint32_t)n_clusters) {     // per-block completion flags (the queue has a tail)
+            a.done = d_done;
+            if (done_armed) *done_armed = true;
+        }
         CK(ctx, bwtc_launch(a, ctx->bwt_threads, C, n_clusters, d.stream));
         d.launches++;
         return BNZ_OK;

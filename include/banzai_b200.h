@@ -163,8 +163,8 @@ typedef struct bnz_stats {
     uint32_t bwt_max_rounds;
     uint32_t bwt_tied_blocks;
     uint64_t bwt_rounds_total;
-    uint64_t bwt_algorithmic_bytes;  /* 9n + sum over rounds: records sorted through HBM * (16 P_r + 36)
-                                        + records sorted inside shared memory * 24   */
+    uint64_t bwt_algorithmic_bytes;  /* 9n + sum over rounds a_r * (16 P_r + 36), P_r = 0 for records sorted
+                                        inside shared memory   */
     uint64_t bwt_cyc_build, bwt_cyc_radix, bwt_cyc_rerank;   /* SM cycles per phase, summed over blocks */
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t bwt_sum_tile;           /* of bwt_sum_active: records sorted inside shared memory (no HBM pass) */
