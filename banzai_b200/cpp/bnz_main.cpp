@@ -165,7 +165,21 @@ int main(int argc, char **argv)
         std::fprintf(stderr, "error during compression: %s\n", e.what());
         return ERR_OUTPUT;
     }
-    if (outf.is_open()) outf.close();
+    if (outf.is_open()) {
+        // the reference flushes its BufWriter and propagates the error before the input may be removed
+        // (main.rs:287-309): a close that fails (quota, NFS) must not cost the only copy of the data
+        outf.close();
+        if (!outf) {
+            std::fprintf(stderr, "error during compression: cannot write %s: %s\n", out_path.c_str(), std::strerror(errno));
+            return ERR_OUTPUT;
+        }
+    } else {
+        std::cout.flush();
+        if (!std::cout) {
+            std::fprintf(stderr, "error during compression: cannot write to stdout\n");
+            return ERR_OUTPUT;
+        }
+    }
 
     const bool keep = inv.keep >= 0 ? inv.keep == 1 : inv.out != Invocation::OUT_NONE;   // main.rs:292-300
     if (!keep && inv.in == Invocation::IN_FILE) {

@@ -69,3 +69,17 @@ def test_round_trip_and_default_delete(tmp_path):
     r = run(str(p))
     assert r.returncode == 0 and not p.exists()
     assert bz2.decompress((tmp_path / "in.txt.bz2").read_bytes()) == data
+
+
+@pytest.mark.gpu
+def test_failing_output_keeps_the_input(tmp_path):
+    """a sink that cannot take the bytes (/dev/full) is an output error (exit 3, main.rs:287-290) and
+    the input is not removed, whatever the delete rule says"""
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full")
+    data = os.urandom(300000)
+    p = tmp_path / "in.bin"
+    p.write_bytes(data)
+    r = run("--remove", "--output", "/dev/full", str(p))
+    assert r.returncode == 3, r.stderr
+    assert p.exists() and p.read_bytes() == data
