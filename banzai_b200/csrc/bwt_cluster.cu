@@ -20,7 +20,7 @@
 //   * one cluster barrier separates consecutive phases (7 + 2 per round).
 #include <cooperative_groups.h>
 
-#include "common.cuh"
+#include "bwt_common.cuh"
 #include "kernels.h"
 
 namespace cg = cooperative_groups;
@@ -28,15 +28,8 @@ namespace cg = cooperative_groups;
 namespace bnz {
 namespace bwtc {
 
-constexpr int TILE = 4096;
-constexpr int BITS = 8;
-constexpr int BINS = 256;
-constexpr int PASSES = 5;
+using namespace bwtk;                          // record layout, digit_of, match_digit (bwt_common.cuh)
 constexpr int CMAX = BWT_CLUSTER_MAX;
-constexpr int IDX_BITS = 20;
-constexpr u32 IDX_MASK = (1u << IDX_BITS) - 1u;
-constexpr u32 RANK_MASK = (1u << 20) - 1u;
-constexpr u32 DONE = 0x80000000u;
 constexpr int MAX_ROUNDS = 40;
 
 struct Ctl {                                   // per cluster, global memory
@@ -66,28 +59,6 @@ struct __align__(128) Smem {
     u32 s_flag;
     u8 present[256];
 };
-
-__device__ __forceinline__ u32 digit_of(u64 rec, int pass) { return (u32)(rec >> (IDX_BITS + pass * BITS)) & 0xffu; }
-
-__device__ __forceinline__ u32 match_digit(u32 d)
-{
-    u32 peers = 0xffffffffu;
-#pragma unroll
-    for (int b = 0; b < BITS; b++) {
-        asm("{\n"
-            ".reg .pred p;\n"
-            ".reg .b32 t, v;\n"
-            "and.b32 t, %1, %2;\n"
-            "setp.ne.u32 p, t, 0;\n"
-            "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
-            "@!p not.b32 v, v;\n"
-            "and.b32 %0, %0, v;\n"
-            "}\n"
-            : "+r"(peers)
-            : "r"(d), "r"(1u << b));
-    }
-    return peers;
-}
 
 struct Chunking {
     u32 len;          // records per chunk (multiple of TILE)

@@ -42,30 +42,22 @@
 //   Last, one pass in index order writes bwt[rank[i]] = S[i-1] (coalesced reads, a one-byte
 //   scatter that covers the block's output at once and merges in L2).
 // DESIGN.md §4 has the measurements behind these choices.
-#include "common.cuh"
+#include "bwt_common.cuh"
 #include "kernels.h"
 
 namespace bnz {
 namespace bwt {
 
+using namespace bwtk;                // record layout, digit_of, match_digit (bwt_common.cuh)
 constexpr int T = 512;               // threads per CTA
 constexpr int NW = T / 32;           // warps per CTA
 constexpr int K = 8;                 // records per thread per tile
-constexpr int TILE = T * K;          // 4096 records = 32 KB
-constexpr int BITS = 8;              // radix digit
-constexpr int BINS = 1 << BITS;
 constexpr int WORDS = BINS / 2;      // packed counter words per warp row (two 16-bit bins per word)
-constexpr int KEY_BITS = 40;
-constexpr int PASSES = KEY_BITS / BITS;
-constexpr int IDX_BITS = 20;
-constexpr u32 IDX_MASK = (1u << IDX_BITS) - 1u;
-constexpr u32 RANK_MASK = (1u << 20) - 1u;
-constexpr u32 DONE = 0x80000000u;
 constexpr int MAX_ROUNDS = 48;
 constexpr int BMW = TILE / 32;       // words of a per-tile bitmap
 constexpr int UPD_SHIFT = 13;        // round-0 rank updates are bucketed by idx >> 13 ...
 constexpr u32 UPD_CHUNK = 1u << UPD_SHIFT;   // ... so that a bucket covers 8192 ranks = 32 KB of rank[]
-static_assert(WORDS <= T && BMW == 128 && NW == 16, "scan layouts below assume 512 threads, 4096-record tiles");
+static_assert(TILE == T * K && WORDS <= T && BMW == 128 && NW == 16, "scan layouts below assume 512 threads, 4096-record tiles");
 
 struct __align__(128) Smem {
     u64 buf0[TILE];                  // TMA landing zone of the global passes | ping buffer of the in-tile sort
@@ -94,8 +86,6 @@ enum { ACC_ACTIVE = 0, ACC_PASSES, ACC_TILE, ACC_CYC_BUILD, ACC_CYC_RADIX, ACC_C
 
 // per-pass digit histograms: built in the (then idle) reorder buffer, parked in global memory
 __device__ __forceinline__ u32 *hist_of(Smem &sm) { return reinterpret_cast<u32 *>(sm.buf1); }
-
-__device__ __forceinline__ u32 digit_of(u64 rec, int pass) { return (u32)(rec >> (IDX_BITS + pass * BITS)) & (u32)(BINS - 1); }
 
 // update record of the deferred rank scatter: [ done:1 rank:20 | idx >> 13 : 8 | 0:7 | idx & 8191 : 13 ]
 __device__ __forceinline__ u64 upd_record(u32 nr, bool done, u32 id)
@@ -168,28 +158,6 @@ __device__ void build_initial(Smem &sm, const u8 *__restrict__ S, u32 n, u64 *ds
     __syncthreads();
     if (threadIdx.x == 0) sm.s_count = n;
     __syncthreads();
-}
-
-// warp-wide "which lanes hold my digit": BITS ballots (match.any costs ~1000 cycles on this part)
-__device__ __forceinline__ u32 match_digit(u32 d)
-{
-    // peers = lanes whose digit equals mine: AND over the digit's bits of XNOR(ballot(bit), my bit).
-    u32 peers = 0xffffffffu;
-#pragma unroll
-    for (int b = 0; b < BITS; b++) {
-        asm("{\n"
-            ".reg .pred p;\n"
-            ".reg .b32 t, v;\n"
-            "and.b32 t, %1, %2;\n"
-            "setp.ne.u32 p, t, 0;\n"
-            "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
-            "@!p not.b32 v, v;\n"
-            "and.b32 %0, %0, v;\n"
-            "}\n"
-            : "+r"(peers)
-            : "r"(d), "r"(1u << b));
-    }
-    return peers;
 }
 
 // Stable rank of this warp's records among the warp's records with the same digit.  The warp owns

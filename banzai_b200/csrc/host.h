@@ -81,6 +81,7 @@ struct Device {
     // arenas (grown on demand, kept across calls)
     DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, ws_hist;
     DevBuf v_marks, v_lfl, v_flags;     // self-verification (verify.cu)
+    DevBuf sel;                         // huff_literal: selectors [nb][sel_stride]
     DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, ch_tiles, rle_blocks, crc_acc;
     DevBuf seg_base, seg_list, seg_cnt, seg_state, num_names, syms, sym_off, sym_len, freqs, mtf_ids, mtf_cseg;
     DevBuf lens, codes, tf, num_tables, num_sel, span_base, hdr, hdr_bits, crc, blk_bits, blk_bitoff,
@@ -123,6 +124,7 @@ struct bnz_ctx {
     // where the shards of the current bnz_encode call may be downloaded as soon as their bit phase is
     // known (several devices, one batch); o == nullptr: the caller packs and downloads afterwards
     struct { uint8_t *o = nullptr; size_t cap = 0; } early_out;
+    int huff_literal = 0;              // run huffman::encode's 4-round table refinement literally (default: its closed form)
     int verify = 0;                    // check every block on the device (and the CRCs on the host) before emitting
     int verify_corrupt = 0;            // test hook: damage an intermediate of block 0 behind the sort's back
     int reuse_input = 0;               // the caller re-encodes the SAME host buffer: keep its device copy resident (benchmarks)

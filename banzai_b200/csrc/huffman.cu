@@ -16,7 +16,11 @@
 //            table_freqs[0] = A_0 + 3 G,  table_freqs[t>0] = A_t,  all selectors = 0,
 //        which is what huff_build_kernel folds in (the tables built after iterations 0..2 are
 //        dead: they are zeroed before use).  tests/test_oracle.py proves this closed form
-//        against the literal loop of the oracle.
+//        against the literal loop of the oracle.  With bnz_ctx_set("huff_literal", 1) the device
+//        runs the reference's loop literally instead (huff_launch_literal: four rounds of
+//        per-group cost / strict-< argmin over the T tables, table_freqs accumulation, table
+//        rebuild, selectors recorded in the last round, symbols coded with selectors[i / 50]);
+//        tests/test_mtf_huff_gpu.py checks that both give the oracle's bits.
 //   Q11  code lengths: the reference's own binary heap with its tie behaviour, priorities
 //        (weight, depth), scaling retry until max length <= 17      huffman.rs:161-298
 //   Q12/13 serialisation order and MSB-first packing               huffman.rs:462-575, out.rs
@@ -110,6 +114,7 @@ __global__ void __launch_bounds__(GT) huff_assign_kernel(HuffArgs a)
         }
         if (s1 != 0xffffu) atomicAdd(&hist[best * MAXS + s1], 1u);
         if (s2 != 0xffffu) atomicAdd(&hist[best * MAXS + s2], 1u);
+        if (a.sel_out && lane == 0) a.sel_out[(size_t)b * a.sel_stride + g] = (u8)best;     // huffman.rs:446-448
     }
     __syncthreads();
     u32 *tf = a.tf + (size_t)b * MAXT * MAXS;
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(BW * 32) huff_build_kernel(HuffArgs a)
     // iterations 1..3 (zeroed tables): every group adds its histogram to table 0
     for (u32 s = lane; s < MAXS; s += 32) {
         u32 v = tf[s];
-        if (t == 0) v += (HUFF_REFINEMENTS - 1) * G[s];
+        if (t == 0 && !a.literal) v += (HUFF_REFINEMENTS - 1) * G[s];
         tf[s] = v;
         fr[w][s] = v;
     }
@@ -394,6 +399,43 @@ __global__ void huff_header_kernel(HuffArgs a)
     a.blk_bits[b] = w.total + sym_bits;
 }
 
+// symbol bits of every block when groups use different tables: sum over the groups of the code
+// lengths of their symbols in the table selectors[g] names (huffman.rs:565-572); added to blk_bits
+__global__ void __launch_bounds__(GT) huff_symbits_kernel(HuffArgs a)
+{
+    __shared__ u8 lens[MAXT * MAXS];
+    __shared__ unsigned long long total;
+    const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    u32 lo = 0, hi = a.n_blocks;
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (a.span_base[mid] <= blockIdx.x) lo = mid; else hi = mid;
+    }
+    const u32 b = lo;
+    const u32 span = blockIdx.x - a.span_base[b];
+    const u32 T = a.num_tables[b];
+    const u32 m = a.sym_len[b];
+    const u16 *syms = a.syms + a.sym_off[b];
+    const u8 *sel = a.selectors + (size_t)b * a.sel_stride;
+    for (u32 i = tid; i < T * MAXS; i += GT) lens[i] = a.lens[(size_t)b * MAXT * MAXS + i];
+    if (tid == 0) total = 0;
+    __syncthreads();
+    const u32 ngroups = (m + GROUP - 1) / GROUP;
+    const u32 g0 = span * GPC, g1 = min(g0 + GPC, ngroups);
+    u32 mine = 0;
+    for (u32 g = g0 + w; g < g1; g += GT / 32) {
+        const u32 base = g * GROUP;
+        const u32 glen = min((u32)GROUP, m - base);
+        const u32 t = sel[g];
+        if (lane < glen) mine += lens[t * MAXS + syms[base + lane]];
+        if (lane + 32 < glen) mine += lens[t * MAXS + syms[base + 32 + lane]];
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0 && mine) atomicAdd(&total, (unsigned long long)mine);
+    __syncthreads();
+    if (tid == 0 && total) atomicAdd(reinterpret_cast<unsigned long long *>(a.blk_bits + b), total);
+}
+
 // exclusive scan of blk_bits -> blk_bitoff (+ base); single CTA
 __global__ void __launch_bounds__(1024) huff_scan_kernel(HuffArgs a)
 {
@@ -530,6 +572,36 @@ cudaError_t huff_launch(const HuffArgs &a, uint32_t total_spans, cudaStream_t st
     huff::huff_header_kernel<<<(a.n_blocks + 31) / 32, 32, 0, st>>>(a);
     huff::huff_scan_kernel<<<1, 1024, 0, st>>>(a);
     if (launches) *launches += 5;
+    return cudaGetLastError();
+}
+
+// huffman::encode's modelling loop run literally (huffman.rs:399-460): HUFF_REFINEMENTS rounds of
+// { zero the tables unless it is the first round; assign every group to its cheapest table and add
+// its histogram to that table's frequencies; rebuild all tables }, selectors recorded in the last
+// round.  `a.selectors` / `a.sel_out` must point to [n_blocks][a.sel_stride] bytes.
+cudaError_t huff_launch_literal(HuffArgs a, uint32_t total_spans, cudaStream_t st, uint32_t *launches)
+{
+    if (a.n_blocks == 0) return cudaSuccess;
+    uint8_t *sel = a.sel_out;
+    const unsigned jobs = a.n_blocks * huff::MAXT;
+    a.literal = 1;
+    a.selectors = nullptr;
+    huff::huff_init_kernel<<<(a.n_blocks + 127) / 128, 128, 0, st>>>(a);
+    for (int it = 0; it < HUFF_REFINEMENTS; it++) {
+        if (it != 0) {
+            cudaError_t e = cudaMemsetAsync(a.lens, 0, (size_t)a.n_blocks * huff::MAXT * huff::MAXS, st);
+            if (e != cudaSuccess) return e;
+        }
+        a.sel_out = (it == HUFF_REFINEMENTS - 1) ? sel : nullptr;
+        huff::huff_assign_kernel<<<total_spans, huff::GT, 0, st>>>(a);
+        huff::huff_build_kernel<<<(jobs + huff::BW - 1) / huff::BW, huff::BW * 32, 0, st>>>(a);
+    }
+    a.sel_out = nullptr;
+    a.selectors = sel;
+    huff::huff_header_kernel<<<(a.n_blocks + 31) / 32, 32, 0, st>>>(a);
+    huff::huff_symbits_kernel<<<total_spans, huff::GT, 0, st>>>(a);
+    huff::huff_scan_kernel<<<1, 1024, 0, st>>>(a);
+    if (launches) *launches += 4 + 2 * HUFF_REFINEMENTS;
     return cudaGetLastError();
 }
 

@@ -159,6 +159,8 @@ struct HuffArgs {
     uint32_t *num_tables;         // [n_blocks]
     uint32_t *num_sel;            // [n_blocks]
     const uint8_t *selectors;     // nullptr: every selector is 0 (SURVEY A-Q10)
+    uint8_t *sel_out;             // literal loop: the assign kernel records the table of every group here
+    int literal;                  // literal loop: table_freqs are used as they are (no closed-form fold)
     size_t sel_stride;
     const uint32_t *span_base;    // [n_blocks + 1] first assign-CTA of each block
     uint32_t *hdr;                // [n_blocks][hdr_stride] header bits as MSB-first words
@@ -176,6 +178,7 @@ struct HuffArgs {
     uint32_t *out_words;          // output stream (zeroed by the host)
 };
 cudaError_t huff_launch(const HuffArgs &a, uint32_t total_spans, cudaStream_t st, uint32_t *launches);
+cudaError_t huff_launch_literal(HuffArgs a, uint32_t total_spans, cudaStream_t st, uint32_t *launches);
 cudaError_t huff_pack_launch(const HuffArgs &a, cudaStream_t st, uint32_t *launches);
 cudaError_t huff_rescan_launch(const HuffArgs &a, cudaStream_t st, uint32_t *launches);
 uint32_t huff_groups_per_span();

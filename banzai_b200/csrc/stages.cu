@@ -473,6 +473,16 @@ int run_huff_model_device(bnz_ctx *ctx, Device &d, const Batch &bt, int level, i
     a.with_block_header = with_block_header;
     a.bit_base = bit_base;
     a.fixed_stride_bits = fixed_stride_bits;
+    if (ctx->huff_literal) {
+        // the reference's modelling loop, literally (one selector byte per 50-symbol group)
+        a.sel_stride = (size_t)(100000 * level + 1 + 49) / 50 + 16;
+        CK(ctx, d.sel.ensure((size_t)nb * a.sel_stride));
+        a.sel_out = d.sel.as<uint8_t>();
+        a.selectors = d.sel.as<uint8_t>();
+        HuffArgs run = a;
+        CK(ctx, huff_launch_literal(run, bt.span_base[nb], d.stream, &d.launches));
+        return BNZ_OK;
+    }
     CK(ctx, huff_launch(a, bt.span_base[nb], d.stream, &d.launches));
     return BNZ_OK;
 }

@@ -55,6 +55,11 @@ BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
  *   "bwt_cluster_below"  auto mode: cluster kernel when a device gets fewer blocks than this (250)
  *   "bwt_threads"        512 | 1024, cluster kernel
  *   "bwt_ctas_per_sm"    0 = auto
+ *   "huff_literal"       1: run the 4-round table refinement of huffman::encode literally on the
+ *                        device (per-group cost and argmin over all tables, rebuild, selectors);
+ *                        0 (default): its closed form for this reference (lib/huffman.rs:399-460
+ *                        zeroes the tables before rounds 1..3, SURVEY A-Q10) — same bits, ~10 ms
+ *                        less per GiB
  *   "verify"             1: self-verification (the reference has no decoder, README.md:9; its safety
  *                        net is the libbz2 round trip of fuzz/fuzz_targets/round_trip.rs): before a
  *                        stream is returned, every block's RLE1 image is decoded back to its input

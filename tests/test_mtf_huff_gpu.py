@@ -100,3 +100,37 @@ def test_huffman_small_alphabets_and_tiny_blocks(ctx):
         s, n, f = O.mtf_and_rle(bw, has)
         mtfs.append((s, n, f))
     _check_huff(ctx, mtfs)
+
+
+def test_huffman_literal_refinement_loop_on_device(ctx):
+    """bnz_ctx_set("huff_literal", 1): the device runs huffman::encode's four refinement rounds
+    literally (lib/huffman.rs:399-460: per-group cost and strict-< argmin over all tables,
+    table_freqs accumulation, rebuild, selectors of the last round) instead of their closed form.
+    Tables, selectors and bits must be the oracle's (whose loop is the literal one)."""
+    mtfs = []
+    for kind in ("text", "binary", "random"):
+        data = corpus.by_name(kind, 899999 + 100000)
+        for d in (data[:899999], data[899999:]):
+            bw, _, has = O.bwt(d)
+            mtfs.append(O.mtf_and_rle(bw, has))
+    for raw in (b"a", b"hello world", bytes(1000), bytes(range(199)) * 3, bytes(range(198)) * 3):
+        bw, _, has = O.bwt(raw)
+        mtfs.append(O.mtf_and_rle(bw, has))
+    ctx.set("huff_literal", 1)
+    try:
+        _check_huff(ctx, mtfs)
+    finally:
+        ctx.set("huff_literal", 0)
+
+
+@pytest.mark.parametrize("level", [1, 9])
+def test_stream_with_literal_refinement(level):
+    import banzai_b200
+    data = corpus.mixed(6 * 1000 * 1000 + 17)
+    want = O.encode_mt(data, level)
+    with banzai_b200.Context(n_gpus=1) as c:
+        c.set("huff_literal", 1)
+        assert c.encode_bytes(data, level) == want
+    with banzai_b200.Context(devices=[0, 0]) as c:
+        c.set("huff_literal", 1)
+        assert c.encode_bytes(data, level) == want
