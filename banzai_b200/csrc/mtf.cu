@@ -10,8 +10,10 @@
 //                 stored (256 B per segment).  The initial list is the present bytes in
 //                 ascending order (lib/mtf.rs:17-24,40-43: names are order preserving, so
 //                 ranking raw bytes instead of names gives identical indices).
-//   M3  apply   : per segment, one thread runs the plain list shuffle (lib/mtf.rs:86-100)
-//                 from its starting list and writes one MTF index byte per position.
+//   M3  apply   : per segment, one thread derives the indices the list shuffle of lib/mtf.rs:86-100
+//                 would give, without shuffling a list: index = number of bytes whose last
+//                 occurrence is more recent than that of the current byte (a popcount over a
+//                 position mask); one MTF index byte per position.
 //   M4  rle2    : per block, a CTA turns index bytes into symbols: index r >= 1 -> r + 1;
 //                 a maximal zero run of length z -> the bits of z + 1 below its top bit,
 //                 LSB first, as RUNA(0)/RUNB(1) (lib/mtf.rs:46-65); EOB = names + 1 closes
@@ -25,7 +27,6 @@ namespace mtf {
 
 constexpr int SEG = MTF_SEG;          // bytes per segment
 constexpr int NT1 = 128;              // threads per CTA in M1 / M3
-constexpr int ROW = 264;              // padded list row in shared memory (8-byte aligned, bank spread)
 
 __device__ __forceinline__ u32 find_block(const u32 *__restrict__ seg_base, u32 n_blocks, u32 seg)
 {
@@ -159,44 +160,66 @@ __global__ void __launch_bounds__(W2 * 32) mtf_compose_kernel(MtfArgs a)
 }
 
 // ------------------------------------------------------------------ M3: apply per segment
-__global__ void __launch_bounds__(NT1) mtf_apply_kernel(MtfArgs a)
+// One thread per segment, but without the recency list: the MTF index of byte c at position p is
+// the number of DISTINCT bytes seen since c's previous occurrence, i.e. the number of bytes whose
+// LAST occurrence lies after last[c].  The thread keeps last[256] (position of the last occurrence
+// of every byte) and a bit mask `alive` over positions (bit q set <=> q is the last occurrence of
+// its byte so far); the starting list of the segment is a virtual prefix of 256 positions (list[0]
+// the most recent).  Index = popcount(alive over (last[c], p)) — one or two mask words for the
+// recent bytes of text, six for the ~180 positions random data looks back, where the list shuffle
+// it replaces walked and shifted up to 32 eight-entry words per byte (17 ms per GiB, 10 of 32 lanes
+// active; profiles/README.md).  The most recent byte is kept in registers (not in the tables)
+// until another byte displaces it, so runs cost two instructions per byte.
+// Tables are transposed in shared memory ([entry][thread]): conflict-free whatever the lanes index.
+constexpr int NT3 = 128;              // threads (segments) per CTA
+constexpr int MW = (256 + SEG) / 32;  // mask words per segment
+
+__global__ void __launch_bounds__(NT3) mtf_apply_kernel(MtfArgs a)
 {
-    extern __shared__ __align__(16) u8 rows[];          // NT1 rows of ROW bytes
-    const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
-    const u32 segc = blockIdx.x * NT1 + tid;             // position in this launch's segment list
-    const bool live = segc < a.total_segs;
-    u32 seg = 0, n = 0, start = 0;
-    const u8 *src = nullptr;
-    u8 *dst = nullptr;
-    if (live) {
-        const u32 bc = find_block(a.cseg_base, a.n_blocks, segc);
-        const u32 s = segc - a.cseg_base[bc];
-        const u32 b = a.ids[bc];
-        seg = a.seg_base[b] + s;
-        n = a.blk_len[b];
-        src = a.bwt + a.blk_off[b];
-        dst = a.idx + a.blk_off[b];
-        start = s * SEG;
-    }
-    // cooperative, coalesced load of the 32 starting lists of this warp
-    for (u32 t = 0; t < 32; t++) {
-        const u32 sg = __shfl_sync(0xffffffffu, seg, t);
-        if (__shfl_sync(0xffffffffu, (u32)live, t)) {
-            uint2 v = *reinterpret_cast<const uint2 *>(a.seg_state + (size_t)sg * 256 + lane * 8);
-            u8 *row = rows + (w * 32 + t) * ROW;
-            *reinterpret_cast<u32 *>(row + lane * 8) = v.x;
-            *reinterpret_cast<u32 *>(row + lane * 8 + 4) = v.y;
-        }
-    }
-    __syncwarp();
-    if (!live) return;
-    const u32 end = min(start + SEG, n);
-    u8 *row = rows + tid * ROW;
-    // list positions 0..7 live in a register (byte i = position i); 8..255 stay in the row
-    u64 hq = 0;
+    extern __shared__ __align__(16) u32 sm3[];
+    u32 *mask = sm3;                                            // mask[w * NT3 + tid]
+    u16 *last = reinterpret_cast<u16 *>(sm3 + MW * NT3);        // last[c * NT3 + tid]
+    const u32 tid = threadIdx.x;
+    const u32 segc = blockIdx.x * NT3 + tid;                     // position in this launch's segment list
+    if (segc >= a.total_segs) return;
+    const u32 bc = find_block(a.cseg_base, a.n_blocks, segc);
+    const u32 s = segc - a.cseg_base[bc];
+    const u32 b = a.ids[bc];
+    const u32 seg = a.seg_base[b] + s;
+    const u32 n = a.blk_len[b];
+    const u8 *src = a.bwt + a.blk_off[b];
+    u8 *dst = a.idx + a.blk_off[b];
+    const u32 start = s * SEG, end = min(start + SEG, n);
+
+    // ---- the starting list as a virtual prefix: list[i] sits at position 255 - i.  Entries behind the
+    // block's nn names are padding: written first, so that a real entry of the same value wins.
+    {
+        const uint4 *row = reinterpret_cast<const uint4 *>(a.seg_state + (size_t)seg * 256);
+        for (int i = 15; i >= 0; i--) {
+            const uint4 v = row[i];
+            const u32 wv[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-    for (int k = 7; k >= 0; k--) hq = (hq << 8) | row[k];
-    const u64 ONES = 0x0101010101010101ull, HIGH = 0x8080808080808080ull;
+            for (int j = 15; j >= 0; j--) {
+                const u32 c = (wv[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+                last[c * NT3 + tid] = (u16)(255 - (i * 16 + j));
+            }
+        }
+        const u32 nn = a.num_names[b];                           // (compose wrote it before this launch)
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            // bits 256 - nn .. 255 alive
+            const int lo = 256 - (int)nn - w * 32;               // first alive bit of this word (may be <= 0 or >= 32)
+            mask[w * NT3 + tid] = lo >= 32 ? 0u : (lo <= 0 ? 0xffffffffu : (0xffffffffu << lo));
+        }
+        for (int w = 8; w < MW; w++) mask[w * NT3 + tid] = 0u;
+    }
+
+    // the most recent byte and its position are kept out of the tables
+    u32 rc = a.seg_state[(size_t)seg * 256];                      // list[0]
+    u32 rpos = 255;
+    {   // take it out of the tables
+        mask[7 * NT3 + tid] &= 0x7fffffffu;
+    }
 
     for (u32 p = start; p < end; p += 16) {
         u32 w4[4];
@@ -208,44 +231,38 @@ __global__ void __launch_bounds__(NT1) mtf_apply_kernel(MtfArgs a)
             for (u32 j = 0; p + j < end; j++) w4[j >> 2] |= (u32)src[p + j] << ((j & 3) * 8);
         }
         u32 o4[4] = { 0, 0, 0, 0 };
+        const u32 base = 256 + (p - start);                      // position of byte 0 of this vector
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-            // a whole word equal to the current front byte is four zero indices: nothing moves
-            if ((j & 3) == 0 && p + j + 4 <= end && w4[j >> 2] == (u32)(hq & 0xff) * 0x01010101u) {
+            // a whole word equal to the current byte is four zero indices: nothing moves
+            if ((j & 3) == 0 && p + j + 4 <= end && w4[j >> 2] == rc * 0x01010101u) {
+                rpos = base + j + 3;
                 j += 3;
                 continue;
             }
             if (p + j < end) {
-                const u64 c = (w4[j >> 2] >> ((j & 3) * 8)) & 0xffu;
-                const u64 x = hq ^ (c * ONES);
-                const u64 z = (x - ONES) & ~x & HIGH;          // lowest set bit marks the first equal byte
-                u32 k;
-                if (z) {
-                    k = (u32)(__ffsll((long long)z) - 1) >> 3;
-                    const u64 m = (k == 7) ? ~0ull : ((1ull << (8 * (k + 1))) - 1ull);
-                    hq = (hq & ~m) | ((hq << 8) & m) | c;
-                } else {
-                    // deeper than the register head: walk the row 8 entries (one 64-bit word) at a time,
-                    // shifting each word up by one entry and carrying its top entry into the next
-                    u64 carry = hq >> 56;
-                    hq = (hq << 8) | c;
-                    u64 *row64 = reinterpret_cast<u64 *>(row);
-                    k = 255;
-                    for (u32 wi = 1; wi < 32; wi++) {
-                        const u64 wv = row64[wi];
-                        const u64 xx = wv ^ (c * ONES);
-                        const u64 zz = (xx - ONES) & ~xx & HIGH;
-                        if (zz) {
-                            const u32 pb = (u32)(__ffsll((long long)zz) - 1) >> 3;
-                            const u64 m = (pb == 7) ? ~0ull : ((1ull << (8 * (pb + 1))) - 1ull);
-                            row64[wi] = (wv & ~m) | (((wv << 8) | carry) & m);
-                            k = wi * 8 + pb;
-                            break;
-                        }
-                        row64[wi] = (wv << 8) | carry;
-                        carry = wv >> 56;
+                const u32 c = (w4[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+                const u32 cur = base + j;
+                u32 k = 0;
+                if (c != rc) {
+                    // commit the displaced byte: it is the last occurrence of rc
+                    mask[(rpos >> 5) * NT3 + tid] |= 1u << (rpos & 31);
+                    last[rc * NT3 + tid] = (u16)rpos;
+                    // alive positions in (lp, cur): every one is a distinct byte more recent than c
+                    const u32 lp = last[c * NT3 + tid];
+                    const u32 lo = lp + 1, hi = cur - 1;          // inclusive range; never empty (rpos = cur - 1 > lp)
+                    const u32 wl = lo >> 5, wr = hi >> 5;
+                    const u32 ml = 0xffffffffu << (lo & 31), mr = 0xffffffffu >> (31 - (hi & 31));
+                    if (wl == wr) {
+                        k = __popc(mask[wl * NT3 + tid] & ml & mr);
+                    } else {
+                        k = __popc(mask[wl * NT3 + tid] & ml) + __popc(mask[wr * NT3 + tid] & mr);
+                        for (u32 w = wl + 1; w < wr; w++) k += __popc(mask[w * NT3 + tid]);
                     }
+                    mask[(lp >> 5) * NT3 + tid] &= ~(1u << (lp & 31));
+                    rc = c;
                 }
+                rpos = cur;
                 o4[j >> 2] |= k << ((j & 3) * 8);
             }
         }
@@ -382,8 +399,12 @@ cudaError_t mtf_launch(const MtfArgs &a, cudaStream_t st, uint32_t *launches)
     unsigned g1 = (a.total_segs + mtf::NT1 - 1) / mtf::NT1;
     mtf::mtf_summary_kernel<<<g1, mtf::NT1, 0, st>>>(a);
     mtf::mtf_compose_kernel<<<(a.n_blocks + mtf::W2 - 1) / mtf::W2, mtf::W2 * 32, 0, st>>>(a);
-    size_t smem = (size_t)mtf::NT1 * mtf::ROW;
-    mtf::mtf_apply_kernel<<<g1, mtf::NT1, smem, st>>>(a);
+    const size_t smem3 = (size_t)mtf::NT3 * (mtf::MW * 4 + 256 * 2);
+    {   // (per device; cheap)
+        cudaError_t e = cudaFuncSetAttribute(mtf::mtf_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+        if (e != cudaSuccess) return e;
+    }
+    mtf::mtf_apply_kernel<<<(a.total_segs + mtf::NT3 - 1) / mtf::NT3, mtf::NT3, smem3, st>>>(a);
     mtf::mtf_rle2_kernel<<<a.n_blocks, mtf::T4, 0, st>>>(a);
     if (launches) *launches += 4;
     return cudaGetLastError();
