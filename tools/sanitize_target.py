@@ -23,11 +23,20 @@ if which in ("all", "encode"):
         assert sink.getvalue() == O.encode(data, 9)
     with banzai_b200.Context(devices=[0, 0]) as ctx:
         assert ctx.encode_bytes(data, 1) == O.encode(data, 1)
+    with banzai_b200.Context(n_gpus=1) as ctx:            # self-verification kernels, literal Huffman loop
+        ctx.set("verify", 1)
+        ctx.set("huff_literal", 1)
+        for cl in (0, 8):
+            ctx.set("bwt_cluster", cl)
+            assert ctx.encode_bytes(data, 9) == O.encode(data, 9)
+        periodic = (b"ab" * 200000)[:399999] + bytes(150000)
+        assert ctx.encode_bytes(periodic, 5) == O.encode(periodic, 5)
 if which in ("all", "bwt"):
     nblk = int(sys.argv[2]) if len(sys.argv) > 2 else 700
     src = corpus.mixed(nblk * 3000)
     blocks = [src[i * 3000:(i + 1) * 3000].tobytes() for i in range(nblk)]
-    blocks += [b"abcdefg" * 500, bytes(4000), (b"ab" * 3000)[:4999]]
+    blocks += [b"abcdefg" * 500, bytes(4000), (b"ab" * 3000)[:4999], (b"ab" * 40000)[:79999],
+               (corpus.random_bytes(1000, seed=3).tobytes() * 80)[:79999]]
     with banzai_b200.Context(n_gpus=1) as ctx:
         for cl in (0, 8):
             ctx.set("bwt_cluster", cl)
