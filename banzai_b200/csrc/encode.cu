@@ -564,8 +564,9 @@ static int encode_sharded(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level
     return BNZ_OK;
 }
 
-// One GPU, host input, many blocks: the input is uploaded and cut in pieces.  The first piece holds
-// about one block per SM; its blocks are sorted (lane 0) while the rest is still on the PCIe bus.
+// One GPU, host input, many blocks: the input is uploaded and cut in pieces.  The first piece is small
+// (7/16 of a block per SM, ~60 MB at level 9: on the device after ~1 ms); its blocks are sorted
+// (lane 0, cluster kernel) while the rest is still on the PCIe bus.
 // The chunk tables of a later piece continue the earlier ones (the scan carries are kept per tile),
 // the host walk is simply repeated over the input so far (1 us per block) and must reproduce the
 // earlier pieces' blocks; the new blocks run on a further lane of the same device, whose sort CTAs
@@ -580,10 +581,10 @@ static int encode_pieces(bnz_ctx *ctx, const uint8_t *h_in, size_t N, int level,
     const uint64_t n_chunks = (N + RLE_CHUNK - 1) / RLE_CHUNK;
     const uint64_t tile = rle_scan_tile_chunks();
     const uint64_t blk = (uint64_t)100000 * level;
-    // piece 0: about one block per SM (rounded up to whole scan tiles).  Its sort CTAs then leave
-    // half of every SM free, so the RLE kernels of the next piece can run as soon as its bytes
-    // have arrived (behind a launch with two CTAs on every SM they waited ~25 ms for the first
-    // blocks to finish), and one CTA per SM already sorts at 87 % of the rate of two.
+    // piece 0: piece_blocks_per_sm_x16 / 16 blocks per SM (rounded up to whole scan tiles): large enough to
+    // keep every SM busy until the second piece has arrived, small enough that its sort is over by
+    // then, so that the RLE kernels of the next piece find free SM slots (measured, 1 GiB: 6..9
+    // sixteenths give 150.4-151.2 ms end to end, 17 gives 153.0, 28 gives 167.0).
     const uint64_t slots = (uint64_t)d0.sm_count * (uint64_t)ctx->piece_blocks_per_sm_x16 / 16;
     uint64_t c0 = ((slots * blk / RLE_CHUNK + tile - 1) / tile) * tile;
     int K = ctx->h2d_pieces;

@@ -118,7 +118,7 @@ struct bnz_ctx {
     int open_streams = 0;
     std::vector<Device *> aux;         // further lanes on the first device (created on demand): the blocks of later input pieces
     int h2d_pieces = 3;                // pieces the input of one call is uploaded in (first piece: see piece_blocks_per_sm_x16)
-    int piece_blocks_per_sm_x16 = 17;  // size of the first piece in blocks per SM (x 1/16)
+    int piece_blocks_per_sm_x16 = 7;   // size of the first piece in blocks per SM (x 1/16): measured best 6..9 (profiles/r2_experiments)
     int h2d_overlap = 1;               // one device, host input: upload in two pieces, sort the first while the second arrives
     int crc_low_prio = 1;              // block CRCs on the low-priority stream (they would delay the start of the sort)
     // where the shards of the current bnz_encode call may be downloaded as soon as their bit phase is

@@ -75,7 +75,7 @@ BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
  *   "h2d_overlap"        1 (default): one GPU, host input of >= 256 MiB: upload in "h2d_pieces" (3)
  *                        pieces and sort each while the next arrives | 0 single upload | 2 forced (tests)
  *   "h2d_pieces"         pieces of that upload (3; one lane of the GPU per piece)
- *   "piece_blocks_per_sm_x16"  size of the first piece in blocks per SM, in sixteenths (17)
+ *   "piece_blocks_per_sm_x16"  size of the first piece in blocks per SM, in sixteenths (7)
  *   "crc_low_prio"       1: block CRCs on the low-priority stream (default) | 0: normal side stream
  *   "max_batch_bytes"    inputs above this (3 GiB) are encoded in batches so that device memory
  *                        stays bounded
