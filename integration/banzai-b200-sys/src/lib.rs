@@ -16,6 +16,13 @@ pub struct BnzStream {
 }
 
 pub const BNZ_OK: c_int = 0;
+pub const BNZ_EINVAL: c_int = 1;
+pub const BNZ_ECUDA: c_int = 2;
+pub const BNZ_ENOMEM: c_int = 3;
+pub const BNZ_EINTERNAL: c_int = 4;
+pub const BNZ_EIO: c_int = 5;
+/// "verify" is on and a block failed the self-check (RLE1 decode, inverse BWT, cut chain, CRC)
+pub const BNZ_EVERIFY: c_int = 6;
 
 pub type BnzSinkFn = extern "C" fn(user: *mut c_void, data: *const u8, len: usize) -> c_int;
 
@@ -24,6 +31,8 @@ extern "C" {
     pub fn bnz_ctx_destroy(ctx: *mut BnzCtx);
     pub fn bnz_strerror(code: c_int) -> *const c_char;
     pub fn bnz_last_error(ctx: *const BnzCtx) -> *const c_char;
+    /// tunables, e.g. `bnz_ctx_set(ctx, c"verify".as_ptr(), 1)` (include/banzai_b200.h lists the keys)
+    pub fn bnz_ctx_set(ctx: *mut BnzCtx, key: *const c_char, value: std::os::raw::c_long) -> c_int;
     pub fn bnz_encode(ctx: *mut BnzCtx, input: *const u8, in_len: usize, level: c_int,
                       out: *mut *mut u8, out_len: *mut usize, consumed: *mut usize) -> c_int;
     pub fn bnz_free(ctx: *mut BnzCtx, p: *mut u8);
