@@ -369,6 +369,59 @@ __device__ void radix_pass(Smem &sm, const u64 *src, u64 *dst, u32 count, int pa
     __syncthreads();
 }
 
+// Scatter one tile of records (K per thread, any arrangement: stability is not needed) into the
+// buckets of digit `pass`, whose running cursors live in sm.cursor: the tile body of radix_pass
+// without the TMA load.  Records of threads beyond the valid ones must be ~0 (they sort last and are
+// not stored); `tile_n` = valid records of the tile.
+__device__ __forceinline__ void partition_tile(Smem &sm, const u64 (&rec)[K], u32 tile_n, int pass, u64 *dst)
+{
+    const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    u32 rk[K];
+    rank_rows(sm, rec, K, pass, rk);
+    __syncthreads();
+    if (tid < WORDS) {
+        u32 run = 0;
+#pragma unroll
+        for (int ww = 0; ww < NW; ww++) {
+            const u32 v = sm.whist[ww][tid];
+            sm.whist[ww][tid] = run;
+            run += v;
+        }
+        const u32 lo = run & 0xffffu, hi = run >> 16, sum = lo + hi;
+        const u32 inc = warp_incl_sum(sum);
+        if (lane == 31) sm.scratch[w] = inc;
+        asm volatile("bar.sync 1, %0;" ::"n"(WORDS) : "memory");
+        u32 woff = 0;
+        for (u32 q = 0; q < w; q++) woff += sm.scratch[q];
+        const u32 ex = woff + inc - sum;
+        const u32 b0 = 2 * tid;
+        const u32 cur0 = sm.cursor[b0], cur1 = sm.cursor[b0 + 1];
+        sm.binoff[b0] = (u16)ex;
+        sm.binoff[b0 + 1] = (u16)(ex + lo);
+        sm.gbase[b0] = cur0 - ex;
+        sm.gbase[b0 + 1] = cur1 - (ex + lo);
+        sm.cursor[b0] = cur0 + lo;
+        sm.cursor[b0 + 1] = cur1 + hi;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const u32 d = digit_of(rec[k], pass);
+        const u32 pos = sm.binoff[d] + ((sm.whist[w][d >> 1] >> ((d & 1u) * 16u)) & 0xffffu) + rk[k];
+        sm.buf1[pos] = rec[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const u32 j = k * T + tid;
+        if (j < tile_n) {
+            const u64 r = sm.buf1[j];
+            st_stream(dst + sm.gbase[digit_of(r, pass)] + j, r);
+        }
+    }
+    __syncthreads();
+}
+
 struct RerankOut {
     u32 active;      // records that still share their key after this step
     u32 splits;      // key heads that are not group heads (new groups created)
@@ -377,8 +430,8 @@ struct RerankOut {
 // Walk records sorted by their 40-bit key (round 0: all of the block, `initial`; later: one group
 // that went through the global passes), assign new ranks, retire singletons, and append the
 // records that stay active to the active list at list[out_pos ...] IN SORTED ORDER.
-// `upd` != nullptr (round 0): instead of scattering the ranks, write one update record per rotation
-// (upd[j] for the j-th sorted record) for apply_ranks_bucketed.
+// `upd` != nullptr (round 0): instead of scattering the ranks, one update record per rotation goes to
+// upd[], bucketed by idx >> 13, for apply_ranks_bucketed.
 // (m_val, m_cnt): the group has m_cnt further members whose rank[idx+h] is m_val; they are not among the
 // records (refine_majority) but take their places in the numbering.
 __device__ RerankOut rerank(Smem &sm, const u64 *src, u32 count, bool initial, u32 *rank, u64 *list, u32 out_pos,
@@ -388,6 +441,13 @@ __device__ RerankOut rerank(Smem &sm, const u64 *src, u32 count, bool initial, u
     u32 carry_grp = 0, carry_key = 0;       // 1-based positions of the latest heads so far
     u32 n_active = 0, n_split = 0;
     const u64 grp_mask = initial ? 0ull : ((u64)RANK_MASK << 20);   // bits of r1 inside key40
+    if (upd) {
+        // the update records are scattered at once into the buckets of apply_ranks_bucketed: bucket b
+        // (the ranks of the positions [8192 b, 8192 b + 8192)) lives at upd[8192 b ...] and receives
+        // exactly its positions, so its cursor starts there and no histogram is needed
+        for (u32 b = tid; b < (u32)BINS; b += T) sm.cursor[b] = min(b << UPD_SHIFT, count);
+        __syncthreads();
+    }
 
     for (u32 base = 0; base < count; base += TILE) {
         const u32 j0 = base + tid * K;
@@ -455,13 +515,10 @@ __device__ RerankOut rerank(Smem &sm, const u64 *src, u32 count, bool initial, u
         }
         n_active += tot_a;
         if (upd) {
+            u64 urec[K];
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                if (flg[k] & 1u) {
-                    const u32 id = idx[k];
-                    st_stream(upd + j0 + k, upd_record(nrv[k], (flg[k] & 2u) != 0, id));
-                }
-            }
+            for (int k = 0; k < K; k++) urec[k] = (flg[k] & 1u) ? upd_record(nrv[k], (flg[k] & 2u) != 0, idx[k]) : ~0ull;
+            partition_tile(sm, urec, min((u32)TILE, count - base), 0, upd);
         } else {
 #pragma unroll
             for (int k = 0; k < K; k++) {
@@ -484,23 +541,17 @@ __device__ RerankOut rerank(Smem &sm, const u64 *src, u32 count, bool initial, u
     return o;
 }
 
-// The ranks of round 0 reach rank[] without random DRAM accesses.  rerank left one update record
-// per rotation, in sorted order; one radix pass by idx >> 13 groups them by 32 KB chunk of rank[]
-// (every bucket holds exactly the 8192 positions of its chunk, so its histogram is known in
-// advance), and every chunk is then assembled in shared memory and written out with coalesced
-// stores.  36 bytes of streaming traffic per rotation instead of a 32-byte sector read + write:
+// The ranks of round 0 reach rank[] without random DRAM accesses.  rerank scattered one update
+// record per rotation into buckets by idx >> 13 (a bucket = the 8192 positions of one 32 KB chunk
+// of rank[], at upd[8192 b ...]; the scatter is the tile body of a radix pass, fused into the
+// re-rank walk); here every chunk is assembled in shared memory and written out with coalesced
+// stores.  20 bytes of streaming traffic per rotation instead of a 32-byte sector read + write:
 // with all CTAs scattering 4-byte ranks at once the kernel was bound by exactly those sectors
 // (profiles/README.md; doing the same in the later rounds costs their in-place refinement and
 // measured slower on the mixed corpus).
-__device__ void apply_ranks_bucketed(Smem &sm, u64 *upd, u64 *tmp, u32 n, u32 *rank, u32 *ghist, u32 &phase)
+__device__ void apply_ranks_bucketed(Smem &sm, const u64 *upd, u32 n, u32 *rank)
 {
     const u32 tid = threadIdx.x;
-    for (int b = tid; b < BINS; b += T) {
-        const u32 lo = (u32)b << UPD_SHIFT;
-        ghist[b] = lo < n ? min(UPD_CHUNK, n - lo) : 0u;        // bucket b lives at tmp[8192 b ...]
-    }
-    __syncthreads();
-    radix_pass(sm, upd, tmp, n, 0, ghist, phase);
     u32 *chunk = reinterpret_cast<u32 *>(sm.buf0);              // 8192 ranks
     for (u32 lo = 0; lo < n; lo += UPD_CHUNK) {
         const u32 len = min(UPD_CHUNK, n - lo);
@@ -508,7 +559,7 @@ __device__ void apply_ranks_bucketed(Smem &sm, u64 *upd, u64 *tmp, u32 n, u32 *r
         for (int k = 0; k < 2 * K; k++) {
             const u32 j = k * T + tid;
             if (j < len) {
-                const u64 e = ld_stream64(tmp + lo + j);
+                const u64 e = ld_stream64(upd + lo + j);
                 chunk[(u32)e & (UPD_CHUNK - 1)] = upd_rank_word(e);
             }
         }
@@ -1095,7 +1146,7 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
             RerankOut ro = rerank(sm, sorted, n, true, rank, list, 0, upd);
             count = ro.active;
             __syncthreads();
-            apply_ranks_bucketed(sm, upd, const_cast<u64 *>(sorted), n, rank, ghist, phase);
+            apply_ranks_bucketed(sm, upd, n, rank);
             acc(ACC_CYC_RERANK, (u64)(clock64() - c0));
         }
 
