@@ -42,7 +42,7 @@ class Stats(C.Structure):
 
 
 class BwtBlockStats(C.Structure):
-    _fields_ = [("n", C.c_uint32), ("rounds", C.c_uint32), ("tied", C.c_uint32), ("pad", C.c_uint32),
+    _fields_ = [("n", C.c_uint32), ("rounds", C.c_uint32), ("tied", C.c_uint32), ("period", C.c_uint32),
                 ("sum_active", C.c_uint64), ("sum_active_passes", C.c_uint64), ("cycles", C.c_uint64),
                 ("sum_tile", C.c_uint64)]
 

@@ -178,7 +178,7 @@ class Context:
                 item = item + ({"rounds": st[b].rounds, "tied": st[b].tied,
                                 "sum_active": st[b].sum_active,
                                 "sum_active_passes": st[b].sum_active_passes,
-                                "cycles": st[b].cycles, "score": st[b].pad},)
+                                "cycles": st[b].cycles, "period": st[b].period},)
             res.append(item)
         return res
 

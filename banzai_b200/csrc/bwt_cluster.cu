@@ -57,6 +57,7 @@ struct __align__(128) Smem {
     u32 scratch[40];
     u32 s_count;
     u32 s_flag;
+    Period per;                                // periodic-run test of the claimed block (CTA 0)
     u8 present[256];
 };
 
@@ -516,6 +517,21 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) bwt_cluster_kernel(BwtA
         const u32 n = a.blk_len[blk];
         u32 *ptr_out = a.ptr + blk;
 
+        if (a.defer_list) {
+            // A block with a long periodic run needs ~log2(n) full rounds here; the one-CTA kernel knows the
+            // order of such rotations in closed form (bwt_common.cuh: Period) and finishes it in two rounds.
+            // Leave it to the follow-up launch of that kernel (stages.cu).
+            if (c == 0) {
+                detect_period<T>(S, n, sm.scratch, &sm.per);
+                if (tid == 0) {
+                    ctl->pad[0] = sm.per.p;
+                    if (sm.per.p != 0) a.defer_list[atomicAdd(a.defer_count, 1u)] = blk;
+                }
+            }
+            cluster.sync();
+            if (__ldcg(&ctl->pad[0]) != 0) continue;
+        }
+
         const Chunking ich = make_chunking(n, C);           // index chunks (key build)
         const u32 ilo = min(n, c * ich.len), ihi = min(n, (c + 1) * ich.len);
         u64 *seg = bufA + (size_t)c * ich.len;              // CTA c's segment of the build output
@@ -613,7 +629,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) bwt_cluster_kernel(BwtA
             st.n = n;
             st.rounds = rounds;
             st.tied = tied ? 1u : 0u;
-            st.pad = 0;
+            st.period = 0;
             st.sum_active = sum_active;
             st.sum_active_passes = sum_active_passes;
             st.sum_tile = 0;

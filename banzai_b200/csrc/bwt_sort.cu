@@ -80,6 +80,7 @@ struct __align__(128) Smem {
     u32 s_min;                       // group-end search
     u32 s_flags[8];                  // per pass: every record has the same digit
     u64 acc[8];                      // per block statistics, kept by thread 0 (see ACC_*)
+    Period per;                      // the block's periodic run (per.p == 0: none), bwt_common.cuh
     u8 present[256];                 // has_byte
 };
 enum { ACC_ACTIVE = 0, ACC_PASSES, ACC_TILE, ACC_CYC_BUILD, ACC_CYC_RADIX, ACC_CYC_RERANK, ACC_CYC_TILE };
@@ -580,6 +581,10 @@ __device__ __forceinline__ void tile_finish(Smem &sm, u64 (&rec)[K], u32 nrows, 
 // inside shared memory.  Returns the number of list records consumed; 0 = the group that starts at
 // list[p] does not fit a tile (nothing was done).  The records that stay active are written back to
 // list[out_pos ...] (out_pos <= p: the compaction is in place), out_pos advances.
+// PERIODIC: the block has a periodic run (sm.per, bwt_common.cuh); a second instantiation, so that the
+// code of ordinary blocks is exactly what it is without that case (in one function the extra branch
+// cost them 17 % more cycles per tile in spills).
+template <bool PERIODIC>
 __device__ u32 refine_tile(Smem &sm, u64 *list, u32 p, u32 count, u32 hm, u32 n, u32 *rank, u32 &out_pos,
                            u32 &n_active, u32 &n_split)
 {
@@ -644,7 +649,50 @@ __device__ u32 refine_tile(Smem &sm, u64 *list, u32 p, u32 count, u32 hm, u32 n,
     const u32 nrows = (tile_n > w * (K * 32)) ? min((u32)K, (tile_n - w * (K * 32) + 31) / 32) : 0u;
 
     // ---- rank[idx + h], group numbers, sort items [ group:12 | rank[idx+h]:20 | idx:20 ]
-    {
+    if (PERIODIC) {
+        // The block has a periodic run (bwt_common.cuh): a group whose members all lie inside the run and
+        // in one class mod p is ordered by index, so its sort key is the index (or its complement) and no
+        // rank is gathered; every member becomes a singleton.  r1tab[g] = [ bad:1 | class:11 | rank:20 ].
+        const u32 ps = sm.per.s, pe = sm.per.e, asc = sm.per.asc;
+        u32 rowbase = woff;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 q = q0 + k * 32;
+            if (q < tile_n) {
+                const u32 g = rowbase + __popc(hb[k] & lanemask_le()) - 1;
+                if ((hb[k] >> lane) & 1u)
+                    sm.r1tab[g] = ((u32)(rec[k] >> IDX_BITS) & RANK_MASK) | (sm.per.cls((u32)rec[k] & IDX_MASK) << 20);
+                rec[k] = ((u64)g << (IDX_BITS + 20)) | ((u32)rec[k] & IDX_MASK);
+            } else {
+                rec[k] = ~0ull;
+            }
+            rowbase += __popc(hb[k]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (rec[k] != ~0ull) {
+                const u32 id = (u32)rec[k] & IDX_MASK, g = (u32)(rec[k] >> (IDX_BITS + 20));
+                if (id < ps || id >= pe || sm.per.cls(id) != ((sm.r1tab[g] >> 20) & 0x7ffu)) atomicOr(&sm.r1tab[g], 0x80000000u);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (rec[k] != ~0ull) {
+                const u32 id = (u32)rec[k] & IDX_MASK, g = (u32)(rec[k] >> (IDX_BITS + 20));
+                u32 r2;
+                if (sm.r1tab[g] >> 31) {
+                    u32 j = id + hm;
+                    if (j >= n) j -= n;
+                    r2 = ld_keep(rank + j) & RANK_MASK;
+                } else {
+                    r2 = asc ? id : (IDX_MASK - id);
+                }
+                rec[k] |= (u64)r2 << IDX_BITS;
+            }
+        }
+    } else {
         u32 r2[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -785,7 +833,7 @@ __device__ __forceinline__ void tile_finish(Smem &sm, u64 (&rec)[K], u32 nrows, 
             const u64 it = fin[q];
             const u32 g = (u32)(it >> (IDX_BITS + 20)) & 0xfffu;
             const u32 id = (u32)it & IDX_MASK;
-            const u32 r1 = valid ? sm.r1tab[g] : 0u;
+            const u32 r1 = valid ? (sm.r1tab[g] & RANK_MASK) : 0u;      // (the upper bits: refine_tile on periodic blocks)
             const u32 nr = r1 + (pk - pg) + ((((u32)(it >> IDX_BITS) & RANK_MASK) > m_val) ? m_cnt : 0u);
             const bool khead = (kbw >> lane) & 1u;
             u32 nxt;                                              // is position q + 1 a key head (or the end)?
@@ -1016,6 +1064,53 @@ __device__ int refine_majority(Smem &sm, u64 *list, u32 p, u32 m, u32 hm, u32 n,
     return 1;
 }
 
+// A group larger than a tile (list[p .. p+m)) of a block with a periodic run (bwt_common.cuh): if its
+// members are exactly the arithmetic progression lo, lo + p, ..., hi inside the run — what a run of
+// period p leaves in one group: "abab..." two groups of n/2 rotations — their final order is their
+// index order (ascending or descending by per.asc), so every member gets its final rank at once: two
+// streaming passes over the group, no gather, no further rounds.  Returns false (nothing done) if the
+// group does not have that shape.
+__device__ bool refine_periodic_big(Smem &sm, const u64 *list, u32 p, u32 m, u32 *rank, u32 &n_split)
+{
+    const u32 tid = threadIdx.x;
+    const u32 pp = sm.per.p, ps = sm.per.s, pe = sm.per.e;
+    const u32 r1 = (u32)(list[p] >> IDX_BITS) & RANK_MASK;
+    const u32 c0 = sm.per.cls((u32)list[p] & IDX_MASK);
+    if (tid == 0) {
+        sm.s_min = 0xffffffffu;
+        sm.s_tot = 0;
+    }
+    __syncthreads();
+    u32 mn = 0xffffffffu, mx = 0;
+    int bad = 0;
+    for (u32 j = tid; j < m; j += T) {
+        const u32 id = (u32)list[p + j] & IDX_MASK;
+        if (id < ps || id >= pe || sm.per.cls(id) != c0) bad = 1;
+        mn = min(mn, id);
+        mx = max(mx, id);
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane_id() == 0) {
+        atomicMin(&sm.s_min, mn);
+        atomicMax(&sm.s_tot, mx);
+    }
+    const int anybad = __syncthreads_or(bad);
+    const u32 lo = sm.s_min, hi = sm.s_tot;
+    __syncthreads();
+    // m distinct indices of one class in [lo, hi] with (hi - lo) / p + 1 == m: every class member in between
+    if (anybad || (u64)(hi - lo) != (u64)(m - 1) * pp) return false;
+    const u32 asc = sm.per.asc;
+    for (u32 j = tid; j < m; j += T) {
+        const u32 id = (u32)list[p + j] & IDX_MASK;
+        const u32 pos = asc ? sm.per.div(id - lo) : sm.per.div(hi - id);
+        st_keep(rank + id, (r1 + pos) | DONE);
+    }
+    if (tid == 0) n_split += m - 1;
+    __syncthreads();
+    return true;
+}
+
 // digit histograms of key records that are already in place (the others of refine_majority)
 __device__ void hist_records(Smem &sm, const u64 *recs, u32 cnt)
 {
@@ -1078,6 +1173,15 @@ __device__ void finalize_ties(Smem &sm, const u64 *list, u32 count, const u8 *__
     if (tid == 0 && zero_tied) *ptr_out = base0 + s0 - 1;
 }
 
+// (a call, not inlined: the test must not disturb the register allocation of the kernel of ordinary blocks)
+__device__ __noinline__ void detect_period_call(const u8 *S, u32 n, u32 *sh, Period *out) { detect_period<T>(S, n, sh, out); }
+
+// PERIODIC = false: the kernel of ordinary blocks.  With a.defer_list it tests every block it claims for a
+// long periodic run and leaves those to the follow-up launch of the PERIODIC = true instantiation, which
+// takes its blocks from a.blk_list and knows the order of such rotations in closed form (bwt_common.cuh:
+// Period).  Two instantiations, because the extra branches cost ordinary blocks 4-5 % (register spills)
+// when both lived in one kernel.
+template <bool PERIODIC>
 __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1098,16 +1202,34 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
     u32 *ghist = a.ws_hist + (size_t)blockIdx.x * BWT_HIST_WORDS;
 
     for (;;) {
-        if (tid == 0) sm.s_block = atomicAdd(a.next_block, 1u);
+        if (tid == 0) {
+            // (the list of a follow-up launch: the blocks the cluster kernel left to this one)
+            const u32 pos = atomicAdd(a.next_block, 1u);
+            const u32 nb = a.n_blocks_dev ? __ldcg(a.n_blocks_dev) : a.n_blocks;
+            sm.s_block = pos >= nb ? 0xffffffffu : (a.blk_list ? __ldcg(a.blk_list + pos) : pos);
+        }
         __syncthreads();
         const u32 blk = sm.s_block;
         __syncthreads();
-        if (blk >= a.n_blocks) break;
+        if (blk == 0xffffffffu) break;
 
         const u8 *S = a.rle + a.blk_off[blk];
         u8 *bwt_out = a.bwt + a.blk_off[blk];
         const u32 n = a.blk_len[blk];
         u32 *ptr_out = a.ptr + blk;
+
+        if (PERIODIC) {
+            detect_period<T>(S, n, sm.scratch, &sm.per);
+        } else {
+            if (a.defer_list) {
+                detect_period_call(S, n, sm.scratch, &sm.per);
+                if (sm.per.p != 0) {                             // (block-uniform)
+                    if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1u)] = blk;
+                    __syncthreads();
+                    continue;
+                }
+            }
+        }
 
         u32 rounds = 1;
         bool tied = false;
@@ -1159,7 +1281,8 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
             rounds++;
             while (p < count) {
                 long long c0 = clock64();
-                const u32 used = refine_tile(sm, list, p, count, hm, n, rank, out_pos, n_act, n_spl);
+                const u32 used = (PERIODIC && sm.per.p != 0) ? refine_tile<true>(sm, list, p, count, hm, n, rank, out_pos, n_act, n_spl)
+                                                             : refine_tile<false>(sm, list, p, count, hm, n, rank, out_pos, n_act, n_spl);
                 if (used) {
                     acc(ACC_TILE, used);
                     acc(ACC_CYC_TILE, (u64)(clock64() - c0));
@@ -1169,6 +1292,12 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
                 // a group larger than a tile: sort it by rank[idx + h] through HBM
                 const u32 ge = group_end(sm, list, p, count, (u32)(list[p] >> IDX_BITS) & RANK_MASK);
                 const u32 m = ge - p;
+                if (PERIODIC && sm.per.p != 0 && refine_periodic_big(sm, list, p, m, rank, n_spl)) {
+                    acc(ACC_TILE, m);
+                    acc(ACC_CYC_TILE, (u64)(clock64() - c0));
+                    p = ge;
+                    continue;
+                }
                 u32 m_val = 0xffffffffu, m_cnt = 0, n_keys = m;
                 const int how = refine_majority(sm, list, p, m, hm, n, rank, bufC, reinterpret_cast<u32 *>(bufD), out_pos, n_act,
                                                 n_spl, &m_val, &m_cnt, &n_keys);
@@ -1236,7 +1365,7 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
             st.n = n;
             st.rounds = rounds;
             st.tied = tied ? 1u : 0u;
-            st.pad = 0;
+            st.period = PERIODIC ? sm.per.p : 0u;
             st.sum_active = sm.acc[ACC_ACTIVE];
             st.sum_active_passes = sm.acc[ACC_PASSES];
             st.sum_tile = sm.acc[ACC_TILE];
@@ -1263,14 +1392,22 @@ size_t bwt_smem_bytes() { return sizeof(bwt::Smem); }
 cudaError_t bwt_max_ctas(int *ctas_per_sm)
 {
     size_t smem = bwt_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(bwt::bwt_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(bwt::bwt_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bwt::bwt_sort_kernel, bwt::T, smem);
+    e = cudaFuncSetAttribute(bwt::bwt_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int p0 = 0, p1 = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p0, bwt::bwt_sort_kernel<false>, bwt::T, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p1, bwt::bwt_sort_kernel<true>, bwt::T, smem);
+    *ctas_per_sm = p0 < p1 ? p0 : p1;
+    return e;
 }
 
-cudaError_t bwt_launch(const BwtArgs &a, int grid, cudaStream_t stream)
+cudaError_t bwt_launch(const BwtArgs &a, int grid, cudaStream_t stream, bool periodic)
 {
-    bwt::bwt_sort_kernel<<<grid, bwt::T, bwt_smem_bytes(), stream>>>(a);
+    if (periodic) bwt::bwt_sort_kernel<true><<<grid, bwt::T, bwt_smem_bytes(), stream>>>(a);
+    else bwt::bwt_sort_kernel<false><<<grid, bwt::T, bwt_smem_bytes(), stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -57,7 +57,7 @@ void device_release(Device &d)
     cudaSetDevice(d.id);
     if (d.stream) cudaStreamSynchronize(d.stream);
     for (DevBuf *b : { &d.in, &d.rle, &d.bwt, &d.blk_off, &d.blk_len, &d.ptr, &d.has_byte,
-                       &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.ws_hist, &d.v_marks, &d.v_lfl, &d.v_flags, &d.sel, &d.ch_lasthead, &d.ch_meta,
+                       &d.bwt_stats, &d.counters, &d.ws_rec, &d.ws_rank, &d.ws_ctl, &d.ws_hist, &d.ws_rec2, &d.ws_rank2, &d.ws_defer, &d.v_marks, &d.v_lfl, &d.v_flags, &d.sel, &d.ch_lasthead, &d.ch_meta,
                        &d.ch_restsum, &d.ch_oin, &d.ch_P, &d.ch_tiles, &d.rle_blocks, &d.crc_acc, &d.seg_base,
                        &d.seg_list, &d.seg_cnt, &d.seg_state, &d.num_names, &d.syms, &d.sym_off,
                        &d.sym_len, &d.freqs, &d.mtf_ids, &d.mtf_cseg, &d.lens, &d.codes, &d.tf, &d.num_tables, &d.num_sel,
@@ -195,6 +195,11 @@ extern "C" int bnz_ctx_set(bnz_ctx *ctx, const char *key, long value)
     if (!strcmp(key, "bwt_cluster_below")) {
         if (value < 0) return BNZ_EINVAL;
         ctx->bwt_cluster_below = (int)value;
+        return BNZ_OK;
+    }
+    if (!strcmp(key, "bwt_periodic")) {
+        if (value != 0 && value != 1) return BNZ_EINVAL;
+        ctx->bwt_periodic = (int)value;
         return BNZ_OK;
     }
     if (!strcmp(key, "bwt_threads")) {

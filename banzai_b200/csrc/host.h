@@ -79,7 +79,7 @@ struct Device {
     cudaStream_t stream2 = nullptr;     // side stream: block CRCs run beside the sort
     cudaStream_t stream3[3] = {};       // low-priority streams: MTF of finished blocks fills the sort's tail
     // arenas (grown on demand, kept across calls)
-    DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, ws_hist;
+    DevBuf in, rle, bwt, blk_off, blk_len, ptr, has_byte, bwt_stats, counters, ws_rec, ws_rank, ws_ctl, ws_hist, ws_rec2, ws_rank2, ws_defer;
     DevBuf v_marks, v_lfl, v_flags;     // self-verification (verify.cu)
     DevBuf sel;                         // huff_literal: selectors [nb][sel_stride]
     DevBuf ch_lasthead, ch_meta, ch_restsum, ch_oin, ch_P, ch_tiles, rle_blocks, crc_acc;
@@ -106,6 +106,7 @@ struct bnz_ctx {
     int bwt_cluster = -1;         // CTAs per bzip2 block (-1: auto, 0/1: single-CTA kernel)
     int bwt_threads = 512;
     int bwt_cluster_below = 250;       // auto mode: cluster kernel when a device gets fewer blocks than this
+    int bwt_periodic = 1;              // closed-form order of periodic runs (bwt_common.cuh: Period); 0 = plain doubling
     // cached pinned output buffer handed to the caller by bnz_encode / returned by bnz_free
     uint8_t *out_cache = nullptr;
     size_t out_cache_cap = 0;

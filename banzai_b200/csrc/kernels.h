@@ -62,7 +62,7 @@ struct BwtStats {                 // per bzip2 block, written by the sort kernel
     uint32_t n;                   // RLE1 length of the block
     uint32_t rounds;              // sort rounds executed (incl. the 5-byte round)
     uint32_t tied;                // 1 if the block had identical rotations (period | n)
-    uint32_t pad;
+    uint32_t period;              // period of the block's periodic run if the sort used one (bwt_common.cuh), else 0
     uint64_t sum_active;          // sum over rounds of records sorted (a_r)
     uint64_t sum_active_passes;   // sum over rounds of (records sorted through HBM) * radix passes executed (P_r)
     uint64_t sum_tile;            // records (summed over rounds) that were sorted inside shared memory (no HBM pass)
@@ -87,11 +87,18 @@ struct BwtArgs {
     void *ws_ctl;                 // cluster kernel only: per cluster BWT_CTL_BYTES of control state
     uint32_t *done;               // optional [n_blocks], host-mapped: set to 1 (release.sys) when a block's outputs are complete
     uint32_t *marks;              // optional [n_blocks][VERIFY_MARKS]: row (sorted position) of the rotations 0, 4096, 8192, ... (verify.cu)
+    // Blocks with a long periodic run (bwt_common.cuh: Period) are left by the first launch (either kernel) to a
+    // follow-up launch of the one-CTA kernel's PERIODIC instantiation, which finishes them in two rounds: the
+    // first launch appends them to defer_list / *defer_count, the follow-up launch takes its blocks from
+    // blk_list[0 .. *n_blocks_dev).  nullptr: not used.
+    uint32_t *defer_list, *defer_count;
+    const uint32_t *blk_list, *n_blocks_dev;
 };
 
 size_t bwt_smem_bytes();
 cudaError_t bwt_max_ctas(int *ctas_per_sm);
-cudaError_t bwt_launch(const BwtArgs &a, int grid, cudaStream_t stream);
+// periodic: the instantiation for the blocks of a.blk_list (blocks with a periodic run, left by the first launch)
+cudaError_t bwt_launch(const BwtArgs &a, int grid, cudaStream_t stream, bool periodic = false);
 // cluster-cooperative variant (bwt_cluster.cu)
 size_t bwtc_smem_bytes(int threads);
 cudaError_t bwtc_max_clusters(int threads, int C, int *n_clusters);

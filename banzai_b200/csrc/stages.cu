@@ -30,6 +30,8 @@ int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt
     a.ws_hist = nullptr;
     a.done = nullptr;
     a.marks = d_marks;
+    a.defer_list = a.defer_count = nullptr;
+    a.blk_list = a.n_blocks_dev = nullptr;
 
     // auto: many blocks -> one persistent CTA per block (best aggregate throughput);
     // few blocks -> one cluster per block so that every SM has work and the randomly accessed
@@ -55,8 +57,41 @@ int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt
             a.done = d_done;
             if (done_armed) *done_armed = true;
         }
+        // blocks with a long periodic run go to a follow-up launch of the one-CTA kernel (bwt_common.cuh: Period;
+        // the launch is unconditional — its block count lives in device memory — and exits at once when the
+        // list is empty, so no host round trip is needed)
+        const bool defer = ctx->bwt_periodic && max_len >= 32768u /* PERIOD_MIN_N */;
+        int grid2 = 0;
+        size_t stride2 = 0;
+        if (defer) {
+            int per_sm = 0;
+            CK(ctx, bwt_max_ctas(&per_sm));                     // (also sets the kernel's shared-memory attribute)
+            if (per_sm <= 0) return fail(ctx, BNZ_ECUDA, "bwt kernel does not fit on an SM");
+            grid2 = (int)std::min<uint64_t>((uint64_t)n_blocks, (uint64_t)d.sm_count);
+            stride2 = ((size_t)max_len + 8191) & ~(size_t)8191;
+            CK(ctx, d.ws_defer.ensure((size_t)n_blocks * sizeof(uint32_t)));
+            CK(ctx, d.ws_rec2.ensure((size_t)grid2 * 3 * stride2 * sizeof(uint64_t)));
+            CK(ctx, d.ws_rank2.ensure((size_t)grid2 * stride2 * sizeof(uint32_t)));
+            CK(ctx, d.ws_hist.ensure((size_t)grid2 * BWT_HIST_WORDS * 4));
+            a.defer_list = d.ws_defer.as<uint32_t>();
+            a.defer_count = d.counters.as<uint32_t>() + 2;
+        }
         CK(ctx, bwtc_launch(a, ctx->bwt_threads, C, n_clusters, d.stream));
         d.launches++;
+        if (defer) {
+            BwtArgs b = a;
+            b.blk_list = a.defer_list;
+            b.n_blocks_dev = a.defer_count;
+            b.defer_list = b.defer_count = nullptr;
+            b.next_block = d.counters.as<uint32_t>() + 1;
+            b.ws_ctl = nullptr;
+            b.ws_hist = d.ws_hist.as<uint32_t>();
+            b.ws_rec = d.ws_rec2.as<uint64_t>();
+            b.ws_rank = d.ws_rank2.as<uint32_t>();
+            b.ws_stride = stride2;
+            CK(ctx, bwt_launch(b, grid2, d.stream, true));
+            d.launches++;
+        }
         return BNZ_OK;
     }
 
@@ -77,8 +112,25 @@ int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt
         a.done = d_done;
         if (done_armed) *done_armed = true;
     }
+    const bool defer = ctx->bwt_periodic && max_len >= 32768u /* PERIOD_MIN_N */;
+    if (defer) {
+        CK(ctx, d.ws_defer.ensure((size_t)n_blocks * sizeof(uint32_t)));
+        a.defer_list = d.ws_defer.as<uint32_t>();
+        a.defer_count = d.counters.as<uint32_t>() + 2;
+    }
     CK(ctx, bwt_launch(a, grid, d.stream));
     d.launches++;
+    if (defer) {
+        // the blocks with a long periodic run, if any (the count lives in device memory: no host round
+        // trip; an empty list costs one launch of CTAs that exit at once); same workspace, stream order
+        BwtArgs b = a;
+        b.blk_list = a.defer_list;
+        b.n_blocks_dev = a.defer_count;
+        b.defer_list = b.defer_count = nullptr;
+        b.next_block = d.counters.as<uint32_t>() + 1;
+        CK(ctx, bwt_launch(b, grid, d.stream, true));
+        d.launches++;
+    }
     return BNZ_OK;
 }
 
@@ -154,7 +206,7 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
             stats_out[b].n = st[b].n;
             stats_out[b].rounds = st[b].rounds;
             stats_out[b].tied = st[b].tied;
-            stats_out[b].pad = 0;
+            stats_out[b].period = st[b].period;
             stats_out[b].sum_tile = st[b].sum_tile;
             stats_out[b].sum_active = st[b].sum_active;
             stats_out[b].sum_active_passes = st[b].sum_active_passes;

@@ -54,6 +54,10 @@ BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
  *   "bwt_cluster"        -1 auto | 0 one CTA per block | 2..16 CTAs (one cluster) per block
  *   "bwt_cluster_below"  auto mode: cluster kernel when a device gets fewer blocks than this (250)
  *   "bwt_threads"        512 | 1024, cluster kernel
+ *   "bwt_periodic"       1 (default): blocks with a long periodic run (zero pages, "abab...", repeated
+ *                        records) are ordered in closed form after the first rounds instead of by ~log2(n)
+ *                        doubling rounds — the reference's SA-IS has no bad case there either (README.md:7);
+ *                        the cluster kernel leaves such blocks to the one-CTA kernel.  0: plain doubling
  *   "bwt_ctas_per_sm"    0 = auto
  *   "huff_literal"       1: run the 4-round table refinement of huffman::encode literally on the
  *                        device (per-group cost and argmin over all tables, rebuild, selectors);
@@ -209,7 +213,7 @@ BNZ_API int bnz_host_cut_chain(const uint8_t *in, size_t in_len, int level, cons
  * block b = blocks[blk_off[b] .. blk_off[b] + blk_len[b]).  Outputs use the same layout.
  * has_byte is [n_blocks][256]. max block length = 100000*level. */
 typedef struct bnz_bwt_block_stats {
-    uint32_t n, rounds, tied, pad;
+    uint32_t n, rounds, tied, period;   /* period: of the periodic run the sort used, 0 = none */
     uint64_t sum_active, sum_active_passes;
     uint64_t cycles;              /* SM cycles the block occupied its CTA / cluster */
     uint64_t sum_tile;            /* of sum_active: records sorted inside shared memory */

@@ -88,3 +88,54 @@ def test_many_blocks_more_than_ctas(ctx):
     data = corpus.mixed(700 * 20000)
     blocks = [data[i * 20000:(i + 1) * 20000].tobytes() for i in range(700)]
     _check(ctx, blocks, level=1)
+
+
+def test_periodic_runs_closed_form(ctx):
+    """Blocks with a long periodic run are ordered in closed form (csrc/bwt_common.cuh: Period) —
+    the reference's SA-IS has no bad case for them (README.md:7).  Runs that do not reach the block's
+    ends (what RLE1 makes of zero pages: partial first and last run), two runs around an odd byte,
+    damaged runs, both directions; the cluster kernel leaves such blocks to the one-CTA kernel."""
+    unit = corpus.random_bytes(1000, seed=corpus.SEED_C3).tobytes()
+    rng = np.random.default_rng(11)
+
+    def noisy(b, k):
+        a = bytearray(b)
+        for pos in rng.integers(0, len(a), k):
+            a[int(pos)] ^= 0x55
+        return bytes(a)
+
+    blocks = [
+        (b"ab" * 450000)[:899999],                                   # a level-9 block, period 2, n odd
+        (b"ba" * 450000)[:899999],                                   # the other direction
+        (b"abcdefg" * 130000)[:899999],
+        (unit * 900)[:899999],
+        b"\x00\x00\x00\x00\x60" + b"\x00\x00\x00\x00\xfb" * 150000 + b"\x00\x00\x00\x00\x17",
+        b"xyz" + b"ab" * 300000 + b"the end",                        # head and tail outside the run
+        b"ab" * 100000 + b"c" + b"ab" * 100000,                      # two runs of one period around an odd byte
+        noisy((unit * 300)[:299999], 3),
+        bytes([1, 0]) * 200000 + bytes([0]),
+        (b"aab" * 300000)[:899998],
+        b"ab" * 20000,                                               # period | n: identical rotations (tie rule)
+        corpus.by_name("text", 60000).tobytes() + b"0123456789" * 30000,   # the run covers the second half only
+    ]
+    want = [O.bwt(b) for b in blocks]
+    for val in (0, 8):
+        ctx.set("bwt_cluster", val)
+        got = ctx.stage_bwt(blocks, 9, with_stats=True)
+        for blk, (bw, ptr, has, st), (ebw, eptr, ehas) in zip(blocks, got, want):
+            assert ptr == eptr, (val, len(blk), st)
+            assert bytes(bw) == bytes(ebw), (val, len(blk), st)
+            assert (has == ehas).all()
+        assert got[0][3]["period"] == 2 and got[0][3]["rounds"] <= 4, got[0][3]
+        assert got[3][3]["period"] == 1000 and got[3][3]["rounds"] <= 4, got[3][3]
+        assert got[4][3]["period"] == 5 and got[4][3]["rounds"] <= 5, got[4][3]
+    # the same bytes from plain doubling
+    ctx.set("bwt_periodic", 0)
+    for val in (0, 8):
+        ctx.set("bwt_cluster", val)
+        got = ctx.stage_bwt(blocks[:5], 9, with_stats=True)
+        for (bw, ptr, has, st), (ebw, eptr, ehas) in zip(got, want):
+            assert ptr == eptr and bytes(bw) == bytes(ebw)
+        assert got[0][3]["period"] == 0 and got[0][3]["rounds"] > 10
+    ctx.set("bwt_periodic", 1)
+    ctx.set("bwt_cluster", -1)
