@@ -82,6 +82,7 @@ struct __align__(128) Smem {
     u64 acc[8];                      // per block statistics, kept by thread 0 (see ACC_*)
     Period per;                      // the block's periodic run (per.p == 0: none), bwt_common.cuh
     u8 present[256];                 // has_byte
+    u8 code[256];                    // build_initial: dense code of every present byte
 };
 enum { ACC_ACTIVE = 0, ACC_PASSES, ACC_TILE, ACC_CYC_BUILD, ACC_CYC_RADIX, ACC_CYC_RERANK, ACC_CYC_TILE };
 
@@ -122,43 +123,106 @@ __device__ __forceinline__ void hist_add(Smem &sm, u64 rec)
     for (int p = 0; p < PASSES; p++) atomicAdd(&hist[p * BINS + digit_of(rec, p)], 1u);
 }
 
-// Round 0: key = the five bytes S[i..i+5) (cyclic), big-endian, so h = 5 afterwards.
+// Round 0: key = the first k symbols of the rotation, S[i..i+k) (cyclic), so h = k afterwards.
+// A block that uses all 256 byte values gets k = 5 raw bytes (40 bits).  A block with a smaller alphabet
+// (text: 55-90 symbols) gets MORE symbols into the same 40 bits: the bytes are replaced by their dense
+// codes 0..sigma-1 (order preserving) and the key is the base-sigma number c0 c1 ... c(k-1) with the
+// largest k such that sigma^k <= 2^40 (k = 6 for sigma <= 101, 7 for <= 52, 8 for <= 32).  The passes are
+// the same five; the first round already separates what differs within k symbols, so fewer rotations
+// stay active and the doubling continues from h = k (measured: DESIGN.md §4).
 // S is 16-byte aligned and padded to 16 bytes, so two aligned 32-bit loads cover any 5-byte window.
-__device__ void build_initial(Smem &sm, const u8 *__restrict__ S, u32 n, u64 *dst)
+// Returns k.
+__device__ __noinline__ u32 build_initial(Smem &sm, const u8 *__restrict__ S, u32 n, u64 *dst)
 {
+    const u32 tid = threadIdx.x;
     hist_clear(sm);
-    for (int i = threadIdx.x; i < 256; i += T) sm.present[i] = 0;
+    for (int i = tid; i < 256; i += T) sm.present[i] = 0;
     __syncthreads();
     const u32 *S32 = reinterpret_cast<const u32 *>(S);
-    for (u32 base = 0; base < n; base += TILE) {
+    // ---- the alphabet
+    for (u32 i = tid * 4; i < n; i += T * 4) {
+        const u32 w = __ldg(S32 + (i >> 2));
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            u32 i = base + k * T + threadIdx.x;
-            if (i < n) {
-                u64 key = 0;
-                if (i + 8 <= n) {
-                    const u32 w0 = __ldg(S32 + (i >> 2)), w1 = __ldg(S32 + (i >> 2) + 1);
-                    const u32 sh = (i & 3) * 8;
-                    const u32 lo = __funnelshift_r(w0, w1, sh);            // bytes i .. i+3 (little endian)
-                    const u32 b4 = (w1 >> sh) & 0xffu;                     // byte i+4
-                    key = ((u64)__byte_perm(lo, 0, 0x0123) << 8) | b4;
-                } else {
-                    u32 q = i;
-                    for (int j = 0; j < 5; j++) {
-                        key = (key << 8) | S[q];
-                        q = (q + 1 == n) ? 0 : q + 1;
+        for (int j = 0; j < 4; j++)
+            if (i + j < n) sm.present[(w >> (8 * j)) & 0xffu] = 1;
+    }
+    __syncthreads();
+    u32 bal = 0;
+    if (tid < 256) {
+        bal = __ballot_sync(0xffffffffu, sm.present[tid] != 0);
+        if (lane_id() == 0) sm.scratch[warp_id()] = __popc(bal);
+    }
+    __syncthreads();
+    u32 sigma = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) sigma += sm.scratch[w];
+    if (tid < 256) {
+        u32 before = 0;
+        for (u32 w = 0; w < warp_id(); w++) before += sm.scratch[w];
+        sm.code[tid] = (u8)(before + __popc(bal & lanemask_lt()));      // (sigma = 256: the identity)
+    }
+    __syncthreads();
+    const u32 k = sigma > 101 ? 5u : sigma > 52 ? 6u : sigma > 32 ? 7u : 8u;
+
+    if (k == 5) {
+        for (u32 base = 0; base < n; base += TILE) {
+#pragma unroll
+            for (int kk = 0; kk < K; kk++) {
+                u32 i = base + kk * T + tid;
+                if (i < n) {
+                    u64 key = 0;
+                    if (i + 8 <= n) {
+                        const u32 w0 = __ldg(S32 + (i >> 2)), w1 = __ldg(S32 + (i >> 2) + 1);
+                        const u32 sh = (i & 3) * 8;
+                        const u32 lo = __funnelshift_r(w0, w1, sh);            // bytes i .. i+3 (little endian)
+                        const u32 b4 = (w1 >> sh) & 0xffu;                     // byte i+4
+                        key = ((u64)__byte_perm(lo, 0, 0x0123) << 8) | b4;
+                    } else {
+                        u32 q = i;
+                        for (int j = 0; j < 5; j++) {
+                            key = (key << 8) | S[q];
+                            q = (q + 1 == n) ? 0 : q + 1;
+                        }
                     }
+                    u64 rec = (key << IDX_BITS) | i;
+                    st_stream(dst + i, rec);
+                    hist_add(sm, rec);
                 }
-                sm.present[(u32)(key >> 32)] = 1;        // first byte = S[i]
-                u64 rec = (key << IDX_BITS) | i;
-                st_stream(dst + i, rec);
-                hist_add(sm, rec);
+            }
+        }
+    } else {
+        for (u32 base = 0; base < n; base += TILE) {
+#pragma unroll 2
+            for (int kk = 0; kk < K; kk++) {
+                u32 i = base + kk * T + tid;
+                if (i < n) {
+                    u64 key = 0;
+                    if (i + 12 <= n) {
+                        const u32 w0 = __ldg(S32 + (i >> 2)), w1 = __ldg(S32 + (i >> 2) + 1), w2 = __ldg(S32 + (i >> 2) + 2);
+                        const u32 sh = (i & 3) * 8;
+                        const u32 lo = __funnelshift_r(w0, w1, sh);            // bytes i .. i+3
+                        const u32 hi = __funnelshift_r(w1, w2, sh);            // bytes i+4 .. i+7
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            if ((u32)j < k) key = key * sigma + sm.code[((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu];
+                    } else {
+                        u32 q = i;
+                        for (u32 j = 0; j < k; j++) {
+                            key = key * sigma + sm.code[S[q]];
+                            q = (q + 1 == n) ? 0 : q + 1;
+                        }
+                    }
+                    u64 rec = (key << IDX_BITS) | i;
+                    st_stream(dst + i, rec);
+                    hist_add(sm, rec);
+                }
             }
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) sm.s_count = n;
+    if (tid == 0) sm.s_count = n;
     __syncthreads();
+    return k;
 }
 
 // Stable rank of this warp's records among the warp's records with the same digit.  The warp owns
@@ -1256,11 +1320,11 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
             return src;
         };
 
-        // ---- round 0: all rotations by their first five bytes
-        u32 count;
+        // ---- round 0: all rotations by their first h0 symbols (5 bytes, or more symbols of a small alphabet)
+        u32 count, h0;
         {
             long long c0 = clock64();
-            build_initial(sm, S, n, bufC);
+            h0 = build_initial(sm, S, n, bufC);
             acc(ACC_CYC_BUILD, (u64)(clock64() - c0));
             const u64 *sorted = sort_keys(n);
             c0 = clock64();
@@ -1273,7 +1337,7 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
         }
 
         // ---- rounds h = 5, 10, 20, ...: refine the groups of the active list
-        u32 h = 5;
+        u32 h = h0;
         while (count > 0 && rounds < MAX_ROUNDS) {
             const u32 hm = h % n;
             u32 p = 0, out_pos = 0, n_act = 0, n_spl = 0, big_spl = 0;

@@ -60,7 +60,9 @@ int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt
         // blocks with a long periodic run go to a follow-up launch of the one-CTA kernel (bwt_common.cuh: Period;
         // the launch is unconditional — its block count lives in device memory — and exits at once when the
         // list is empty, so no host round trip is needed)
-        const bool defer = ctx->bwt_periodic && max_len >= 32768u /* PERIOD_MIN_N */;
+        // Only when the clusters need more than one wave: a single wave of clusters does the ~19 rounds of such a
+        // block in about the time one CTA alone needs for its two (measured, 2 blocks: 7.2 against 12.2 ms).
+        const bool defer = ctx->bwt_periodic && max_len >= 32768u /* PERIOD_MIN_N */ && n_blocks > (uint32_t)n_clusters;
         int grid2 = 0;
         size_t stride2 = 0;
         if (defer) {

@@ -120,9 +120,11 @@ def test_periodic_runs_closed_form(ctx):
     ]
     want = [O.bwt(b) for b in blocks]
     for val in (0, 8):
+        # (the cluster kernel hands such blocks over only when its clusters need more than one wave)
+        rep = 1 if val == 0 else 4
         ctx.set("bwt_cluster", val)
-        got = ctx.stage_bwt(blocks, 9, with_stats=True)
-        for blk, (bw, ptr, has, st), (ebw, eptr, ehas) in zip(blocks, got, want):
+        got = ctx.stage_bwt(blocks * rep, 9, with_stats=True)
+        for blk, (bw, ptr, has, st), (ebw, eptr, ehas) in zip(blocks * rep, got, want * rep):
             assert ptr == eptr, (val, len(blk), st)
             assert bytes(bw) == bytes(ebw), (val, len(blk), st)
             assert (has == ehas).all()
