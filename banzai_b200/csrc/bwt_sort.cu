@@ -83,6 +83,7 @@ struct __align__(128) Smem {
     Period per;                      // the block's periodic run (per.p == 0: none), bwt_common.cuh
     u8 present[256];                 // has_byte
     u8 code[256];                    // build_initial: dense code of every present byte
+    u8 code2[256];                   // build_initial: the code coarsened to the levels left in the key
 };
 enum { ACC_ACTIVE = 0, ACC_PASSES, ACC_TILE, ACC_CYC_BUILD, ACC_CYC_RADIX, ACC_CYC_RERANK, ACC_CYC_TILE };
 
@@ -127,9 +128,12 @@ __device__ __forceinline__ void hist_add(Smem &sm, u64 rec)
 // A block that uses all 256 byte values gets k = 5 raw bytes (40 bits).  A block with a smaller alphabet
 // (text: 55-90 symbols) gets MORE symbols into the same 40 bits: the bytes are replaced by their dense
 // codes 0..sigma-1 (order preserving) and the key is the base-sigma number c0 c1 ... c(k-1) with the
-// largest k such that sigma^k <= 2^40 (k = 6 for sigma <= 101, 7 for <= 52, 8 for <= 32).  The passes are
-// the same five; the first round already separates what differs within k symbols, so fewer rotations
-// stay active and the doubling continues from h = k (measured: DESIGN.md §4).
+// largest k such that sigma^k <= 2^40 (k = 6 for sigma <= 101, 7 for <= 52, 8 for <= 32); what is left
+// of the 40 bits holds the NEXT symbol coarsened to L = floor(2^40 / sigma^k) levels (text, sigma = 56:
+// 35 levels, nearly a seventh symbol).  That is sound: the doubling only needs ranks that are consistent
+// with the true order and whose ties imply equal h-prefixes; extra information splits more groups.
+// The passes are the same five; the first round already separates what differs within k symbols, so
+// fewer rotations stay active and the doubling continues from h = k (measured: DESIGN.md §4).
 // S is 16-byte aligned and padded to 16 bytes, so two aligned 32-bit loads cover any 5-byte window.
 // Returns k.
 __device__ __noinline__ u32 build_initial(Smem &sm, const u8 *__restrict__ S, u32 n, u64 *dst)
@@ -163,6 +167,12 @@ __device__ __noinline__ u32 build_initial(Smem &sm, const u8 *__restrict__ S, u3
     }
     __syncthreads();
     const u32 k = sigma > 101 ? 5u : sigma > 52 ? 6u : sigma > 32 ? 7u : 8u;
+    u64 pw = 1;
+    for (u32 j = 0; j < k; j++) pw *= sigma;
+    const u64 room = (1ull << KEY_BITS) / pw;
+    const u32 L = room < (u64)sigma ? (u32)room : sigma;         // levels of the coarse next symbol (1: none)
+    if (tid < 256) sm.code2[tid] = (u8)(((u32)sm.code[tid] * L) / sigma);
+    __syncthreads();
 
     if (k == 5) {
         for (u32 base = 0; base < n; base += TILE) {
@@ -202,15 +212,22 @@ __device__ __noinline__ u32 build_initial(Smem &sm, const u8 *__restrict__ S, u3
                         const u32 sh = (i & 3) * 8;
                         const u32 lo = __funnelshift_r(w0, w1, sh);            // bytes i .. i+3
                         const u32 hi = __funnelshift_r(w1, w2, sh);            // bytes i+4 .. i+7
+                        const u32 b8 = (w2 >> sh) & 0xffu;                     // byte i+8
+                        u32 nx = b8;                                           // the symbol after the k-th
 #pragma unroll
-                        for (int j = 0; j < 8; j++)
-                            if ((u32)j < k) key = key * sigma + sm.code[((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu];
+                        for (int j = 0; j < 8; j++) {
+                            const u32 b = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu;
+                            if ((u32)j < k) key = key * sigma + sm.code[b];
+                            else if ((u32)j == k) nx = b;
+                        }
+                        key = key * L + sm.code2[nx];
                     } else {
                         u32 q = i;
                         for (u32 j = 0; j < k; j++) {
                             key = key * sigma + sm.code[S[q]];
                             q = (q + 1 == n) ? 0 : q + 1;
                         }
+                        key = key * L + sm.code2[S[q]];
                     }
                     u64 rec = (key << IDX_BITS) | i;
                     st_stream(dst + i, rec);
