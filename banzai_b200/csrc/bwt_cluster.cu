@@ -58,6 +58,7 @@ struct __align__(128) Smem {
     u32 s_count;
     u32 s_flag;
     Period per;                                // periodic-run test of the claimed block (CTA 0)
+    KeyCode kc;                                // how the round-0 key packs the block's alphabet (bwt_common.cuh)
     u8 present[256];
 };
 
@@ -109,18 +110,7 @@ __device__ u32 build_initial(Smem<T> &sm, const u8 *__restrict__ S, u32 n, u32 l
         for (int k = 0; k < K; k++) {
             u32 i = base + k * T + threadIdx.x;
             if (i < hi) {
-                u64 key = 0;
-                if (i + 5 <= n) {
-#pragma unroll
-                    for (int j = 0; j < 5; j++) key = (key << 8) | S[i + j];
-                } else {
-                    u32 q = i;
-                    for (int j = 0; j < 5; j++) {
-                        key = (key << 8) | S[q];
-                        q = (q + 1 == n) ? 0 : q + 1;
-                    }
-                }
-                sm.present[(u32)(key >> 32)] = 1;
+                const u64 key = (sm.kc.k == 5) ? raw_key5(S, n, i) : packed_key(S, n, i, sm.kc);
                 u64 rec = (key << IDX_BITS) | i;
                 st_stream(seg + (i - lo), rec);
                 atomicAdd(&sm.nhist[c][digit_of(rec, 0)], 1u);
@@ -536,10 +526,13 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) bwt_cluster_kernel(BwtA
         const u32 ilo = min(n, c * ich.len), ihi = min(n, (c + 1) * ich.len);
         u64 *seg = bufA + (size_t)c * ich.len;              // CTA c's segment of the build output
 
+        // every CTA derives the block's alphabet itself (S comes from L2; no exchange needed)
+        build_alphabet<T>(S, n, sm.present, &sm.kc, sm.scratch);
+
         u32 rounds = 0, tseq = 0, rpar = 0;
         u64 sum_active = 0, sum_active_passes = 0;
         long long cyc_build = 0, cyc_radix = 0, cyc_rerank = 0, t0, t1;
-        u32 h = 5;
+        u32 h = sm.kc.k;
         bool initial = true, tied = false;
 
         while (rounds < MAX_ROUNDS) {

@@ -41,6 +41,113 @@ __device__ __forceinline__ u32 match_digit(u32 d)
     return peers;
 }
 
+// ---- round-0 keys: as many symbols as fit KEY_BITS ------------------------------------------------
+// A block that uses (nearly) all 256 byte values gets k = 5 raw bytes.  A block with a smaller alphabet
+// (text: 55-90 symbols) gets MORE symbols into the same 40 bits: bytes are replaced by their dense codes
+// 0..sigma-1 (order preserving) and the key is the base-sigma number c0 c1 ... c(k-1) with the largest k
+// such that sigma^k <= 2^40 (k = 6 for sigma <= 101, 7 for <= 52, 8 for <= 32); what is left of the 40
+// bits holds the NEXT symbol coarsened to L = floor(2^40 / sigma^k) levels (text, sigma = 56: 35 levels,
+// nearly a seventh symbol).  That is sound: the doubling only needs ranks that are consistent with the
+// true order and whose ties imply equal h-prefixes (h = k); extra information merely splits more groups.
+// The first round then already separates what differs within k symbols, fewer rotations stay active and
+// the doubling continues from h = k (measured: DESIGN.md §4).
+struct KeyCode {
+    u32 sigma, k, L;
+    u8 code[256];        // dense code of every present byte
+    u8 code2[256];       // the code coarsened to L levels
+};
+
+// present[256] (0/1, cleared by the caller) := the bytes of S; *kc := the packing.  All NT >= 256 threads.
+template <int NT>
+__device__ void build_alphabet(const u8 *__restrict__ S, u32 n, u8 *present, KeyCode *kc, u32 *sh)
+{
+    const u32 tid = threadIdx.x;
+    const u32 *S32 = reinterpret_cast<const u32 *>(S);
+    for (u32 i = tid * 4; i < n; i += NT * 4) {
+        const u32 w = __ldg(S32 + (i >> 2));
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (i + j < n) present[(w >> (8 * j)) & 0xffu] = 1;
+    }
+    __syncthreads();
+    u32 bal = 0;
+    if (tid < 256) {
+        bal = __ballot_sync(0xffffffffu, present[tid] != 0);
+        if ((tid & 31u) == 0) sh[tid >> 5] = __popc(bal);
+    }
+    __syncthreads();
+    u32 sigma = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) sigma += sh[w];
+    const u32 k = sigma > 101 ? 5u : sigma > 52 ? 6u : sigma > 32 ? 7u : 8u;
+    u64 pw = 1;
+    for (u32 j = 0; j < k; j++) pw *= sigma;
+    const u64 room = (1ull << KEY_BITS) / pw;
+    const u32 L = room < (u64)sigma ? (u32)room : sigma;      // levels of the coarse next symbol (1: none)
+    if (tid < 256) {
+        u32 before = 0;
+        for (u32 w = 0; w < (tid >> 5); w++) before += sh[w];
+        const u32 c = before + __popc(bal & ((1u << (tid & 31u)) - 1u));
+        kc->code[tid] = (u8)c;                                // (sigma = 256: the identity)
+        kc->code2[tid] = (u8)((c * L) / sigma);
+    }
+    if (tid == 0) {
+        kc->sigma = sigma;
+        kc->k = k;
+        kc->L = L;
+    }
+    __syncthreads();
+}
+
+// key of rotation i.  S is 16-byte aligned and padded to 16 bytes (aligned 32-bit loads cover the window).
+__device__ __forceinline__ u64 raw_key5(const u8 *__restrict__ S, u32 n, u32 i)
+{
+    const u32 *S32 = reinterpret_cast<const u32 *>(S);
+    u64 key = 0;
+    if (i + 8 <= n) {
+        const u32 w0 = __ldg(S32 + (i >> 2)), w1 = __ldg(S32 + (i >> 2) + 1);
+        const u32 sh = (i & 3) * 8;
+        const u32 lo = __funnelshift_r(w0, w1, sh);            // bytes i .. i+3 (little endian)
+        const u32 b4 = (w1 >> sh) & 0xffu;                     // byte i+4
+        key = ((u64)__byte_perm(lo, 0, 0x0123) << 8) | b4;
+    } else {
+        u32 q = i;
+        for (int j = 0; j < 5; j++) {
+            key = (key << 8) | S[q];
+            q = (q + 1 == n) ? 0 : q + 1;
+        }
+    }
+    return key;
+}
+__device__ __forceinline__ u64 packed_key(const u8 *__restrict__ S, u32 n, u32 i, const KeyCode &kc)
+{
+    const u32 *S32 = reinterpret_cast<const u32 *>(S);
+    const u32 sigma = kc.sigma, k = kc.k;
+    u64 key = 0;
+    if (i + 12 <= n) {
+        const u32 w0 = __ldg(S32 + (i >> 2)), w1 = __ldg(S32 + (i >> 2) + 1), w2 = __ldg(S32 + (i >> 2) + 2);
+        const u32 sh = (i & 3) * 8;
+        const u32 lo = __funnelshift_r(w0, w1, sh);            // bytes i .. i+3
+        const u32 hi = __funnelshift_r(w1, w2, sh);            // bytes i+4 .. i+7
+        u32 nx = (w2 >> sh) & 0xffu;                           // byte i+8: the symbol after the k-th if k = 8
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const u32 b = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu;
+            if ((u32)j < k) key = key * sigma + kc.code[b];
+            else if ((u32)j == k) nx = b;
+        }
+        key = key * kc.L + kc.code2[nx];
+    } else {
+        u32 q = i;
+        for (u32 j = 0; j < k; j++) {
+            key = key * sigma + kc.code[S[q]];
+            q = (q + 1 == n) ? 0 : q + 1;
+        }
+        key = key * kc.L + kc.code2[S[q]];
+    }
+    return key;
+}
+
 // ---- blocks with a long periodic run (zero pages after RLE1, "abab...", a repeated record) ----------
 // The reference's SA-IS has no bad case for them (README.md:7); prefix doubling needs log2(n) rounds,
 // because the rotations i, i + p, i + 2p, ... of a run with period p agree until the run ends.  But their

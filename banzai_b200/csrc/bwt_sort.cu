@@ -12,12 +12,14 @@
 // 3 rounds do not wait for blocks that need 20.
 //
 // Per block of n bytes S (n <= 900 000 < 2^20):
-//   round 0 : 64-bit records [ key:40 | idx:20 ], key = S[i..i+5) (cyclic); five LSD radix
+//   round 0 : 64-bit records [ key:40 | idx:20 ], key = the first k symbols of the rotation: 5 raw
+//             bytes, or 6-8 symbols of a smaller alphabet packed base-sigma plus a coarse next symbol
+//             (bwt_common.cuh: KeyCode), h = k afterwards; five LSD radix
 //             passes through HBM (TMA-streamed tiles, see radix_pass); the re-rank step gives
 //             every rotation the position of its group's first record as rank[i] and leaves the
-//             ACTIVE LIST: the records [ rank:20 | idx:20 ] of all rotations whose 5-byte key is
+//             ACTIVE LIST: the records [ rank:20 | idx:20 ] of all rotations whose key is
 //             shared, in sorted order, so that every group is a contiguous run of the list.
-//   round h : (h = 5, 10, 20, ...) a group only has to be sorted by rank[idx + h] WITHIN
+//   round h : (h = k, 2k, 4k, ...) a group only has to be sorted by rank[idx + h] WITHIN
 //             itself.  The list is walked in tiles of whole groups (<= 4096 records): one
 //             coalesced read of the list, one gather of rank[idx + h], a stable LSD radix sort of
 //             (group number in tile : 12, rank[idx+h] : 20) entirely in shared memory, new ranks
@@ -82,8 +84,7 @@ struct __align__(128) Smem {
     u64 acc[8];                      // per block statistics, kept by thread 0 (see ACC_*)
     Period per;                      // the block's periodic run (per.p == 0: none), bwt_common.cuh
     u8 present[256];                 // has_byte
-    u8 code[256];                    // build_initial: dense code of every present byte
-    u8 code2[256];                   // build_initial: the code coarsened to the levels left in the key
+    KeyCode kc;                      // build_initial: how the round-0 key packs the block's alphabet
 };
 enum { ACC_ACTIVE = 0, ACC_PASSES, ACC_TILE, ACC_CYC_BUILD, ACC_CYC_RADIX, ACC_CYC_RERANK, ACC_CYC_TILE };
 
@@ -124,17 +125,7 @@ __device__ __forceinline__ void hist_add(Smem &sm, u64 rec)
     for (int p = 0; p < PASSES; p++) atomicAdd(&hist[p * BINS + digit_of(rec, p)], 1u);
 }
 
-// Round 0: key = the first k symbols of the rotation, S[i..i+k) (cyclic), so h = k afterwards.
-// A block that uses all 256 byte values gets k = 5 raw bytes (40 bits).  A block with a smaller alphabet
-// (text: 55-90 symbols) gets MORE symbols into the same 40 bits: the bytes are replaced by their dense
-// codes 0..sigma-1 (order preserving) and the key is the base-sigma number c0 c1 ... c(k-1) with the
-// largest k such that sigma^k <= 2^40 (k = 6 for sigma <= 101, 7 for <= 52, 8 for <= 32); what is left
-// of the 40 bits holds the NEXT symbol coarsened to L = floor(2^40 / sigma^k) levels (text, sigma = 56:
-// 35 levels, nearly a seventh symbol).  That is sound: the doubling only needs ranks that are consistent
-// with the true order and whose ties imply equal h-prefixes; extra information splits more groups.
-// The passes are the same five; the first round already separates what differs within k symbols, so
-// fewer rotations stay active and the doubling continues from h = k (measured: DESIGN.md §4).
-// S is 16-byte aligned and padded to 16 bytes, so two aligned 32-bit loads cover any 5-byte window.
+// Round 0: key = the first k symbols of the rotation (bwt_common.cuh: KeyCode), so h = k afterwards.
 // Returns k.
 __device__ __noinline__ u32 build_initial(Smem &sm, const u8 *__restrict__ S, u32 n, u64 *dst)
 {
@@ -142,59 +133,15 @@ __device__ __noinline__ u32 build_initial(Smem &sm, const u8 *__restrict__ S, u3
     hist_clear(sm);
     for (int i = tid; i < 256; i += T) sm.present[i] = 0;
     __syncthreads();
-    const u32 *S32 = reinterpret_cast<const u32 *>(S);
-    // ---- the alphabet
-    for (u32 i = tid * 4; i < n; i += T * 4) {
-        const u32 w = __ldg(S32 + (i >> 2));
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (i + j < n) sm.present[(w >> (8 * j)) & 0xffu] = 1;
-    }
-    __syncthreads();
-    u32 bal = 0;
-    if (tid < 256) {
-        bal = __ballot_sync(0xffffffffu, sm.present[tid] != 0);
-        if (lane_id() == 0) sm.scratch[warp_id()] = __popc(bal);
-    }
-    __syncthreads();
-    u32 sigma = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) sigma += sm.scratch[w];
-    if (tid < 256) {
-        u32 before = 0;
-        for (u32 w = 0; w < warp_id(); w++) before += sm.scratch[w];
-        sm.code[tid] = (u8)(before + __popc(bal & lanemask_lt()));      // (sigma = 256: the identity)
-    }
-    __syncthreads();
-    const u32 k = sigma > 101 ? 5u : sigma > 52 ? 6u : sigma > 32 ? 7u : 8u;
-    u64 pw = 1;
-    for (u32 j = 0; j < k; j++) pw *= sigma;
-    const u64 room = (1ull << KEY_BITS) / pw;
-    const u32 L = room < (u64)sigma ? (u32)room : sigma;         // levels of the coarse next symbol (1: none)
-    if (tid < 256) sm.code2[tid] = (u8)(((u32)sm.code[tid] * L) / sigma);
-    __syncthreads();
-
+    build_alphabet<T>(S, n, sm.present, &sm.kc, sm.scratch);
+    const u32 k = sm.kc.k;
     if (k == 5) {
         for (u32 base = 0; base < n; base += TILE) {
 #pragma unroll
             for (int kk = 0; kk < K; kk++) {
-                u32 i = base + kk * T + tid;
+                const u32 i = base + kk * T + tid;
                 if (i < n) {
-                    u64 key = 0;
-                    if (i + 8 <= n) {
-                        const u32 w0 = __ldg(S32 + (i >> 2)), w1 = __ldg(S32 + (i >> 2) + 1);
-                        const u32 sh = (i & 3) * 8;
-                        const u32 lo = __funnelshift_r(w0, w1, sh);            // bytes i .. i+3 (little endian)
-                        const u32 b4 = (w1 >> sh) & 0xffu;                     // byte i+4
-                        key = ((u64)__byte_perm(lo, 0, 0x0123) << 8) | b4;
-                    } else {
-                        u32 q = i;
-                        for (int j = 0; j < 5; j++) {
-                            key = (key << 8) | S[q];
-                            q = (q + 1 == n) ? 0 : q + 1;
-                        }
-                    }
-                    u64 rec = (key << IDX_BITS) | i;
+                    const u64 rec = (raw_key5(S, n, i) << IDX_BITS) | i;
                     st_stream(dst + i, rec);
                     hist_add(sm, rec);
                 }
@@ -204,32 +151,9 @@ __device__ __noinline__ u32 build_initial(Smem &sm, const u8 *__restrict__ S, u3
         for (u32 base = 0; base < n; base += TILE) {
 #pragma unroll 2
             for (int kk = 0; kk < K; kk++) {
-                u32 i = base + kk * T + tid;
+                const u32 i = base + kk * T + tid;
                 if (i < n) {
-                    u64 key = 0;
-                    if (i + 12 <= n) {
-                        const u32 w0 = __ldg(S32 + (i >> 2)), w1 = __ldg(S32 + (i >> 2) + 1), w2 = __ldg(S32 + (i >> 2) + 2);
-                        const u32 sh = (i & 3) * 8;
-                        const u32 lo = __funnelshift_r(w0, w1, sh);            // bytes i .. i+3
-                        const u32 hi = __funnelshift_r(w1, w2, sh);            // bytes i+4 .. i+7
-                        const u32 b8 = (w2 >> sh) & 0xffu;                     // byte i+8
-                        u32 nx = b8;                                           // the symbol after the k-th
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const u32 b = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu;
-                            if ((u32)j < k) key = key * sigma + sm.code[b];
-                            else if ((u32)j == k) nx = b;
-                        }
-                        key = key * L + sm.code2[nx];
-                    } else {
-                        u32 q = i;
-                        for (u32 j = 0; j < k; j++) {
-                            key = key * sigma + sm.code[S[q]];
-                            q = (q + 1 == n) ? 0 : q + 1;
-                        }
-                        key = key * L + sm.code2[S[q]];
-                    }
-                    u64 rec = (key << IDX_BITS) | i;
+                    const u64 rec = (packed_key(S, n, i, sm.kc) << IDX_BITS) | i;
                     st_stream(dst + i, rec);
                     hist_add(sm, rec);
                 }
