@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(W2 * 32) mtf_compose_kernel(MtfArgs a)
 // active; profiles/README.md).  The most recent byte is kept in registers (not in the tables)
 // until another byte displaces it, so runs cost two instructions per byte.
 // Tables are transposed in shared memory ([entry][thread]): conflict-free whatever the lanes index.
-constexpr int NT3 = 128;              // threads (segments) per CTA
+constexpr int NT3 = 160;              // threads (segments) per CTA: 672 B of tables each, two CTAs = 10 warps per SM (128: 8 warps)
 constexpr int MW = (256 + SEG) / 32;  // mask words per segment
 
 __global__ void __launch_bounds__(NT3) mtf_apply_kernel(MtfArgs a)
