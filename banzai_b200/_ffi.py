@@ -34,7 +34,7 @@ class Stats(C.Structure):
         ("bwt_rounds_total", C.c_uint64), ("bwt_algorithmic_bytes", C.c_uint64),
         ("bwt_cyc_build", C.c_uint64), ("bwt_cyc_radix", C.c_uint64), ("bwt_cyc_rerank", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-        ("bwt_sum_tile", C.c_uint64), ("bwt_cyc_tile", C.c_uint64),
+        ("bwt_sum_tile", C.c_uint64), ("bwt_cyc_tile", C.c_uint64), ("bwt_cyc_final", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(T, (T == 512 ? 2 : 1)) bwt_cluster_kernel(BwtA
             st.sum_active_passes = sum_active_passes;
             st.sum_tile = 0;
             st.cyc_tile = 0;
+            st.cyc_final = 0;
             st.cyc_build = (u64)cyc_build;
             st.cyc_radix = (u64)cyc_radix;
             st.cyc_rerank = (u64)cyc_rerank;

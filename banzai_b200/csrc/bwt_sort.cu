@@ -86,7 +86,7 @@ struct __align__(128) Smem {
     u8 present[256];                 // has_byte
     KeyCode kc;                      // build_initial: how the round-0 key packs the block's alphabet
 };
-enum { ACC_ACTIVE = 0, ACC_PASSES, ACC_TILE, ACC_CYC_BUILD, ACC_CYC_RADIX, ACC_CYC_RERANK, ACC_CYC_TILE };
+enum { ACC_ACTIVE = 0, ACC_PASSES, ACC_TILE, ACC_CYC_BUILD, ACC_CYC_RADIX, ACC_CYC_RERANK, ACC_CYC_TILE, ACC_CYC_FINAL };
 
 // per-pass digit histograms: built in the (then idle) reorder buffer, parked in global memory
 __device__ __forceinline__ u32 *hist_of(Smem &sm) { return reinterpret_cast<u32 *>(sm.buf1); }
@@ -1344,6 +1344,7 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
         // within this one short pass, so the sectors fill up in L2 instead of costing a 32-byte
         // DRAM gather per rotation inside the re-rank steps.
         __syncthreads();
+        const long long cf0 = clock64();
         for (u32 base = 0; base < n; base += 4 * T) {
             u32 r[4], c[4];
 #pragma unroll
@@ -1363,6 +1364,7 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
                 if (a.marks && i < n && (i % VERIFY_SPACING) == 0) a.marks[(size_t)blk * VERIFY_MARKS + i / VERIFY_SPACING] = r[k] & RANK_MASK;
             }
         }
+        acc(ACC_CYC_FINAL, (u64)(clock64() - cf0));
         if (tid == 0 && (rank[0] & DONE)) *ptr_out = rank[0] & RANK_MASK;
         if (tid < 256) a.has_byte[(size_t)blk * 256 + tid] = sm.present[tid];
         if (tid == 0 && a.stats) {
@@ -1378,6 +1380,7 @@ __global__ void __launch_bounds__(T, 2) bwt_sort_kernel(BwtArgs a)
             st.cyc_radix = sm.acc[ACC_CYC_RADIX];
             st.cyc_rerank = sm.acc[ACC_CYC_RERANK];
             st.cyc_tile = sm.acc[ACC_CYC_TILE];
+            st.cyc_final = sm.acc[ACC_CYC_FINAL];
             a.stats[blk] = st;
         }
         __syncthreads();

@@ -179,6 +179,7 @@ static void add_stats(bnz_stats &st, const Shard &sh)
         st.bwt_sum_active_passes += b.sum_active_passes;
         st.bwt_sum_tile += b.sum_tile;
         st.bwt_cyc_tile += b.cyc_tile;
+        st.bwt_cyc_final += b.cyc_final;
         st.bwt_rounds_total += b.rounds;
         st.bwt_max_rounds = std::max(st.bwt_max_rounds, b.rounds);
         st.bwt_tied_blocks += b.tied;

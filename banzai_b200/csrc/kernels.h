@@ -67,6 +67,7 @@ struct BwtStats {                 // per bzip2 block, written by the sort kernel
     uint64_t sum_active_passes;   // sum over rounds of (records sorted through HBM) * radix passes executed (P_r)
     uint64_t sum_tile;            // records (summed over rounds) that were sorted inside shared memory (no HBM pass)
     uint64_t cyc_build, cyc_radix, cyc_rerank, cyc_tile;   // SM cycles spent per phase (thread 0's clock64)
+    uint64_t cyc_final;           // ... and in the last pass (bwt[rank[i]] = S[i-1]); one-CTA kernel only
 };
 
 constexpr int BWT_HIST_WORDS = 5 * 1024;

@@ -198,6 +198,7 @@ extern "C" int bnz_stage_bwt(bnz_ctx *ctx, const uint8_t *blocks, const uint64_t
         s.bwt_sum_active_passes += st[b].sum_active_passes;
         s.bwt_sum_tile += st[b].sum_tile;
         s.bwt_cyc_tile += st[b].cyc_tile;
+        s.bwt_cyc_final += st[b].cyc_final;
         s.bwt_rounds_total += st[b].rounds;
         s.bwt_max_rounds = std::max(s.bwt_max_rounds, st[b].rounds);
         s.bwt_tied_blocks += st[b].tied;

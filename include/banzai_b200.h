@@ -178,6 +178,7 @@ typedef struct bnz_stats {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t bwt_sum_tile;           /* of bwt_sum_active: records sorted inside shared memory (no HBM pass) */
     uint64_t bwt_cyc_tile;           /* SM cycles of that path */
+    uint64_t bwt_cyc_final;          /* SM cycles of the sort's last pass (bwt[rank[i]] = S[i-1]) */
 } bnz_stats;
 BNZ_API int bnz_get_stats(const bnz_ctx *ctx, bnz_stats *out);
 
