@@ -168,13 +168,27 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, u3
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// L2 eviction-priority hints (the policy words createpolicy.fractional.L2::evict_* 1.0 produces).
-// Sort records stream through HBM once per pass: evict_first keeps them from flushing the
-// randomly accessed rank[] / S arrays out of the 126 MB L2.
+// L2 eviction-priority hints.  Sort records stream through HBM once per pass: evict_first keeps them
+// from flushing the randomly accessed rank[] / S arrays out of the 126 MB L2.  The policy words come
+// from createpolicy (ptxas turns it into a few uniform-datapath instructions outside the loops that
+// build 0x12F0... / 0x14F0... in a uniform register pair; not volatile, so it is hoisted and shared).
 #ifndef BWT_L2HINT
 #define BWT_L2HINT 2
 #endif
-constexpr u64 L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ u64 l2_evict_first()
+{
+    u64 p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 l2_evict_last()
+{
+    u64 p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#define L2_EVICT_FIRST (l2_evict_first())
+#define L2_EVICT_LAST (l2_evict_last())
 __device__ __forceinline__ void tma_load_1d_stream(void *smem_dst, const void *gsrc, u32 bytes, u64 *bar)
 {
 #if BWT_L2HINT >= 1
