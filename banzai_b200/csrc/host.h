@@ -105,7 +105,8 @@ struct bnz_ctx {
     int ctas_per_sm = 0;
     int bwt_cluster = -1;         // CTAs per bzip2 block (-1: auto, 0/1: single-CTA kernel)
     int bwt_threads = 512;
-    int bwt_cluster_below = 250;       // auto mode: cluster kernel when a device gets fewer blocks than this
+    int bwt_cluster_below = 128;       // auto mode: cluster kernel when a device gets fewer blocks than this (measured crossover ~115
+                                       // level-9 blocks with the packed-key kernels: 137 blocks 22.1 vs 25.6 ms, profiles/r2_experiments)
     int bwt_periodic = 1;              // closed-form order of periodic runs (bwt_common.cuh: Period); 0 = plain doubling
     // cached pinned output buffer handed to the caller by bnz_encode / returned by bnz_free
     uint8_t *out_cache = nullptr;

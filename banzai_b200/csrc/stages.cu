@@ -35,7 +35,8 @@ int run_bwt_device(bnz_ctx *ctx, Device &d, const uint8_t *d_rle, uint8_t *d_bwt
 
     // auto: many blocks -> one persistent CTA per block (best aggregate throughput);
     // few blocks -> one cluster per block so that every SM has work and the randomly accessed
-    // arrays stay in L2 (measured crossover ~250 blocks per device, tools/bwt_blocks_sweep.py)
+    // arrays stay in L2 (measured crossover ~115 blocks per device with the final kernels of round 2,
+    // profiles/r2_experiments/cluster_vs_one_cta_by_blocks.txt)
     int C = ctx->bwt_cluster;
     if (C < 0) C = (n_blocks >= (uint32_t)ctx->bwt_cluster_below) ? 0 : (n_blocks <= 40 ? 16 : 8);
     if (C > 1) {

@@ -52,7 +52,7 @@ BNZ_API const char *bnz_last_error(const bnz_ctx *ctx);
 
 /* tunables (call before encoding). keys:
  *   "bwt_cluster"        -1 auto | 0 one CTA per block | 2..16 CTAs (one cluster) per block
- *   "bwt_cluster_below"  auto mode: cluster kernel when a device gets fewer blocks than this (250)
+ *   "bwt_cluster_below"  auto mode: cluster kernel when a device gets fewer blocks than this (128)
  *   "bwt_threads"        512 | 1024, cluster kernel
  *   "bwt_periodic"       1 (default): blocks with a long periodic run (zero pages, "abab...", repeated
  *                        records) are ordered in closed form after the first rounds instead of by ~log2(n)
